@@ -1,0 +1,161 @@
+/* sequoia_b200 -- C ABI of the B200-native Sequoia hot path (libsequoia_b200.so).
+ *
+ * The reference (Infini-AI-Lab/Sequoia) has no FFI layer: its boundary is the Python class API
+ * (Engine.GraphInferenceEngine[TG], Tree.SpecTree / GreedyTree, utils.*).  This header is the
+ * boundary a maintainer would bind from those classes (ctypes stub in INTEGRATION.md).  Each
+ * entry point cites the reference code it replaces (paths relative to the Sequoia repo).
+ *
+ * Conventions: every function returns SQ_OK (0) or a negative SQ_ERR_* code and records a message
+ * retrievable with sq_last_error(); all pointers are DEVICE pointers unless named host_*; no
+ * ownership transfer; `stream` is a cudaStream_t passed as void*; every launch is asynchronous and
+ * CUDA-graph capturable (no allocation, no synchronisation).  fp16 = IEEE binary16 (`uint16_t` bits).
+ *
+ * "Tree-relative" addressing: many calls take (state, n0).  If `state` is non-NULL the first row of
+ * the call lives at absolute slot  state[SQ_ST_P] - 1 + n0  (tree node n0 of the current iteration:
+ * node k sits at slot P-1+k); if `state` is NULL the first row is slot n0.
+ * This lets a captured graph follow the dynamic prefix length P without host involvement.
+ */
+#ifndef SEQUOIA_B200_H_
+#define SEQUOIA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQ_OK 0
+#define SQ_ERR_INVALID_ARG (-1)
+#define SQ_ERR_CUDA (-2)
+#define SQ_ERR_UNSUPPORTED (-3)
+
+/* words of the int32 device state array (>= SQ_ST_WORDS entries) */
+#define SQ_ST_P 0
+#define SQ_ST_ACCEPT_LEN 1
+#define SQ_ST_TERMINAL 2
+#define SQ_ST_N_NEW 3
+#define SQ_ST_P_OLD 4
+#define SQ_ST_BONUS 5
+#define SQ_ST_NAN 6
+#define SQ_ST_SKIPPED 7
+#define SQ_ST_WORDS 16
+
+typedef uint16_t sq_half;
+
+const char* sq_last_error(void);
+int sq_version(void);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+uint64_t sq_launch_count(void);
+
+/* ---- element-wise model ops (Engine/Llama_modules.py:259-288,327-349; Llama_model.py:53-72) ---- */
+
+/* out[r,:] = table[tokens[base+r],:]   (nn.Embedding, Llama_model.py:53) */
+int sq_embed_rows(const sq_half* table, const int64_t* tokens, const int32_t* state, int n0, int n, int hidden,
+                  sq_half* out, void* stream);
+/* LlamaRMSNorm_FI (Llama_modules.py:274-288): fp32 variance, cast to fp16, then weight * x (fp16). */
+int sq_rmsnorm(const sq_half* x, const sq_half* weight, sq_half* out, int n, int hidden, float eps, void* stream);
+/* resid += delta (fp16 add, Llama_modules.py:341,347) ; out = rmsnorm(resid).  out may be NULL (add only). */
+int sq_add_rmsnorm(sq_half* resid, const sq_half* delta, const sq_half* weight, sq_half* out, int n, int hidden,
+                   float eps, void* stream);
+/* LlamaMLP_FI (Llama_modules.py:270-272): out = fp16(silu(gate)) * up, gate_up = [gate | up] rows of 2*inter. */
+int sq_silu_mul(const sq_half* gate_up, sq_half* out, int n, int inter, void* stream);
+
+/* RoPE (transformers 4.36 apply_rotary_pos_emb, Llama_modules.py:117-118,213-214) applied in place to the
+ * Q columns of the fused qkv rows, and K (rotated) + V appended to the cache at storage slots
+ * (KV_Cache.update_kv_cache, Llama_KV.py:72-89).  qkv row layout: [H*D q | Hkv*D k | Hkv*D v], row pitch ld.
+ * cos/sin: (max_pos, D) fp16 caches (Llama_modules.py:16-45).  position_ids / storage_ids are indexed at
+ * base + r (see tree-relative addressing).  k_layer / v_layer: (Hkv, M, D) of this layer. */
+int sq_rope_kv_append(sq_half* qkv, int ld, int H, int Hkv, int D, const sq_half* cos, const sq_half* sin,
+                      const int64_t* position_ids, const int64_t* storage_ids, const int32_t* state, int n0, int n,
+                      sq_half* k_layer, sq_half* v_layer, int M, void* stream);
+
+/* ---- KV cache (Engine/Llama_KV.py) ---- */
+
+/* gather_kv_incremental (Llama_KV.py:60-68): cache[..., offset+j, :] = cache[..., idx[j], :] for j < n, all
+ * layers/heads, in place with gather-then-copy semantics.  n and offset come from the host values, or -- when
+ * `state` is non-NULL -- from state[SQ_ST_N_NEW] / state[SQ_ST_P_OLD] (device-driven, graph static);
+ * max_n bounds n for the launch.  zero_tail != 0 also zeroes rows >= offset+n like the reference does.
+ * k_cache / v_cache: (L, 1, Hkv, M, D). */
+int sq_kv_gather(sq_half* k_cache, sq_half* v_cache, int L, int Hkv, int M, int D, const int32_t* idx, int n,
+                 int offset, const int32_t* state, int max_n, int zero_tail, void* stream);
+
+/* ---- tree-masked attention (Llama_modules.py:127-134 draft SDPA, :220-248 target explicit attention) ---- */
+
+/* Opaque plan: TMA descriptors + split-KV workspace for one (q buffer, cache) pair.  Host call, not capturable;
+ * create once per engine / width and reuse inside graphs. */
+typedef struct sq_attn_plan sq_attn_plan;
+/* q: (n_max rows, ld) fp16 with head h at columns [h*D,(h+1)*D); k_cache/v_cache: (L,1,Hkv,M,D);
+ * out: (n_max, H*D) fp16.  workspace: device buffer of sq_attn_workspace_bytes(...) bytes. */
+int64_t sq_attn_workspace_bytes(int n_max, int H, int D, int M);
+int sq_attn_plan_create(sq_attn_plan** plan, const sq_half* q, int ld, int n_max, int H, int Hkv, int D,
+                        const sq_half* k_cache, const sq_half* v_cache, int L, int M, sq_half* out,
+                        void* workspace, int64_t workspace_bytes);
+int sq_attn_plan_destroy(sq_attn_plan* plan);
+/* Synchronous: returns the watchdog word of the plan (0 = no tensor-core / TMA wait ever timed out). */
+int sq_attn_plan_error(sq_attn_plan* plan);
+
+/* Attention of n query rows (slots base..base+n-1) of `layer` against cache slots [0, kv_len).
+ *   kv_len = (state ? state[P]-1 : 0) + kv_end          (device-driven when state != NULL)
+ * Mask, one of:
+ *   dense_mask != NULL: additive fp16 mask, row r at dense_mask + r*mask_ld, kv_len columns  (reference semantics);
+ *   else structured tree mask: key slot c is visible from row slot s iff
+ *        c <= min(s, P-1)  ||  (s >= P && c >= P-1 && bit(tree_bits, s-(P-1), c-(P-1)))
+ *   where tree_bits is the growmap's ancestor-or-self matrix packed 32 columns per word, row pitch
+ *   tree_words, tree_size S; with state == NULL, P = prefix_len_host.
+ * scale = 1/sqrt(D).  impl: 0 = tcgen05/TMA kernel (product), 1 = SIMT cross-check kernel (tests only). */
+int sq_tree_attn(sq_attn_plan* plan, int layer, int n, const int32_t* state, int n0, int kv_end,
+                 int prefix_len_host, const sq_half* dense_mask, int64_t mask_ld, const uint32_t* tree_bits,
+                 int tree_words, int tree_size, int impl, void* stream);
+
+/* ---- sampling (utils.py) ---- */
+
+/* out = fp16(softmax(fp16(logits / T)))  (Tree/SpecTree.py:198).  rows of V, pitches in elements. */
+int sq_softmax_T(const sq_half* logits, int64_t ld_in, sq_half* out, int64_t ld_out, int n, int V, float T,
+                 void* stream);
+
+/* One tree level of drafting (Tree/SpecTree.py:103-104 / GreedyTree.py:102-103 + tests/testbed.py:277-285):
+ * for each parent row j < n_parents, top-k (k = k_max) of
+ *     mode 0: fp16(log(rand_row)) / softmax(fp16(logits_row / T))     (utils.py:10-18, exponential race, all fp16)
+ *     mode 1: logits_row                                              (utils.py:29-32, sampling_argmax)
+ * in descending order (ties: lower vocabulary index first), written to positions[j*k_max + i] (may be NULL),
+ * and the first n_branch[j] of them to tokens[base + child_first[j] + i]  (tokens may be NULL).
+ * logits row = logits + parent_rows[j]*ld (parent_rows NULL => row j); rand likewise.  V <= 32768, V % 8 == 0. */
+int sq_sample_level(const sq_half* logits, int64_t ld_logits, const sq_half* rand, int64_t ld_rand,
+                    const int32_t* parent_rows, const int32_t* child_first, const int32_t* n_branch, int n_parents,
+                    int k_max, int V, float T, int mode, int64_t* positions, int64_t* tokens, const int32_t* state,
+                    void* stream);
+
+/* get_residual (utils.py:5-8): out = relu(p-q) / sum(relu(p-q)), fp16 roundings as torch. */
+int sq_residual(const sq_half* p, const sq_half* q, sq_half* out, int V, void* stream);
+
+/* argmax over V per row -> int64 (GreedyTree.py:186). */
+int sq_argmax_rows(const sq_half* logits, int64_t ld, int n, int V, int64_t* out, void* stream);
+
+/* ---- verification walk (Tree/SpecTree.py:137-157,196-227,261-281; GreedyTree.py:132-146,186-240) ---- */
+
+/* Static tree tables on the device (built once per growmap): succ_off (S+1) / succ (CSR children, node ids),
+ * depth (S) int32.  */
+/* Stochastic accept/reject walk from the root, entirely on the device (one CTA):
+ *   p = softmax(fp16(target_logits[cur] / T)); for child c of cur in Successors order:
+ *       q = softmax(fp16(draft_logits[cur] / T)); accept iff p[tok] > fp16(r[slot(c)] * q[tok])  (strict >)
+ *       else p = get_residual(p, q); draft_logits[cur][tok] = fp16 min
+ *   terminal on accepted token in {0, 2} or NaN residual; bonus = argmax(fp16(residual / noise)) (the n=1 form of
+ *   torch.multinomial; `noise` = Exp(1) fp16 row generated by torch).
+ * Then (SpecTree.py:224, 261-271): compact tokens / position_ids, write the bonus token, re-lay tree positions,
+ * and publish state[] (P, accept_len, terminal, n_new, P_old, bonus, nan, skipped) and accept_idx[0..n_new).
+ * target_logits: (S, V) raw logits rows (row k = node k).  draft_logits: (>=S, V) rows, READ ONLY (the masking
+ * of rejected tokens is kept on chip; the reference's in-place edit is dead state).  */
+int sq_accept_stochastic(const sq_half* target_logits, int64_t ld_t, const sq_half* draft_logits, int64_t ld_d,
+                         const sq_half* r, const sq_half* noise, const int32_t* succ_off, const int32_t* succ,
+                         const int32_t* depth, int S, int V, float T, int64_t* tokens, int64_t* position_ids,
+                         int32_t* accept_idx, int32_t* state, int max_target_seq, void* stream);
+/* Greedy walk (GreedyTree.py): target_token (S) int64 from sq_argmax_rows; accept the first child whose token
+ * equals target_token[cur]; bonus = target_token[last accepted]. Same outputs as above. */
+int sq_accept_greedy(const int64_t* target_token, const int32_t* succ_off, const int32_t* succ,
+                     const int32_t* depth, int S, int64_t* tokens, int64_t* position_ids, int32_t* accept_idx,
+                     int32_t* state, int max_target_seq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQUOIA_B200_H_ */

@@ -1,0 +1,288 @@
+// Device-side verification walk (Tree/SpecTree.py:137-157,196-227,261-271; Tree/GreedyTree.py:132-146,186-240).
+// The reference walks the tree on the host with one D2H sync per tested child and ~6 tiny kernels each; here one
+// CTA keeps the target row p, the draft-logit row and the residual in registers, walks Successors (CSR), and then
+// applies the whole post-processing (token / position compaction, bonus token, state for the next iteration), so a
+// verify step needs no host round trip.  Latency-bound: ~2*V*2 bytes per visited parent.
+#include "sq_common.cuh"
+
+namespace sq {
+
+constexpr int ANT = 512;
+constexpr int ANW = ANT / 32;
+constexpr float FP16_MIN = -65504.f;
+
+__device__ __forceinline__ uint32_t a_ord16(__half h) {
+  const uint32_t b = __half_as_ushort(h);
+  return (b & 0x8000u) ? (~b & 0xFFFFu) : (b | 0x8000u);
+}
+
+template <int CH>
+__device__ __forceinline__ void a_load_row(const __half* __restrict__ row, int V, Pack8 (&x)[CH]) {
+  const int nvec = V / 8;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = i * ANT + threadIdx.x;
+    if (c < nvec) x[i].u = reinterpret_cast<const uint4*>(row)[c];
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void a_stats(const Pack8 (&x)[CH], int V, float T, float* red, float& mx, float& sum) {
+  const int nvec = V / 8;
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+    if (i * ANT + threadIdx.x < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m = fmaxf(m, rnd16(h2f(x[i].h[j]) / T));
+    }
+  mx = block_max<ANW>(m, red);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+    if (i * ANT + threadIdx.x < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += expf(rnd16(h2f(x[i].h[j]) / T) - mx);
+    }
+  sum = block_sum<ANW>(s, red);
+}
+
+__device__ __forceinline__ __half a_softmax_val(__half x, float T, float mx, float sum) {
+  return f2h(expf(rnd16(h2f(x) / T) - mx) / sum);
+}
+
+// Post-processing shared by both walks.  Runs with the whole block; thread 0 does the (short, ordered) serial part.
+// sh_acc[0..n_new) = accepted absolute slots; returns nothing, publishes state[].
+__device__ void finish_verify(const int32_t* sh_acc, int n_new, int P, bool terminal, bool nan_flag, int64_t bonus,
+                              const int32_t* __restrict__ depth, int S, int64_t* __restrict__ tokens,
+                              int64_t* __restrict__ position_ids, int32_t* __restrict__ accept_idx,
+                              int32_t* __restrict__ state, int max_target_seq) {
+  const int a = P + n_new;
+  const bool prepare = !terminal && (a + 1 <= max_target_seq);
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < n_new; ++j) {                       // tokens[:a] = tokens[accept_list]  (SpecTree.py:224)
+      const int src = sh_acc[j];
+      accept_idx[j] = src;
+      tokens[P + j] = tokens[src];
+    }
+    if (!terminal) tokens[a] = bonus;                       // SpecTree.py:222 / GreedyTree.py:207
+    if (prepare) {                                          // prepare_for_next_iter (SpecTree.py:261-271)
+      for (int j = 0; j < n_new; ++j) position_ids[P + j] = position_ids[sh_acc[j]];
+      position_ids[a] = a;
+    }
+    state[ST_ACCEPT_LEN] = a;
+    state[ST_TERMINAL] = terminal ? 1 : 0;
+    state[ST_N_NEW] = n_new;
+    state[ST_P_OLD] = P;
+    state[ST_BONUS] = terminal ? -1 : (int32_t)bonus;
+    state[ST_NAN] = nan_flag ? 1 : 0;
+    state[ST_SKIPPED] = (!terminal && !prepare) ? 1 : 0;
+    if (prepare) state[ST_P] = a + 1;
+  }
+  if (prepare) {
+    for (int k = 1 + threadIdx.x; k < S; k += blockDim.x) position_ids[a + k] = (int64_t)depth[k] + a;
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(ANT) accept_stochastic_kernel(
+    const __half* __restrict__ target_logits, int64_t ld_t, const __half* __restrict__ draft_logits, int64_t ld_d,
+    const __half* __restrict__ r, const __half* __restrict__ noise, const int32_t* __restrict__ succ_off,
+    const int32_t* __restrict__ succ, const int32_t* __restrict__ depth, int S, int V, float T,
+    int64_t* __restrict__ tokens, int64_t* __restrict__ position_ids, int32_t* __restrict__ accept_idx,
+    int32_t* __restrict__ state, int max_target_seq) {
+  __shared__ float red[ANW];
+  __shared__ uint32_t redu[ANW];
+  __shared__ int32_t sh_acc[1024];
+  __shared__ int sh_flag;
+  const int P = state[ST_P];
+  const int nvec = V / 8;
+  Pack8 p[CH], dl[CH];
+  int cur = 0, n_new = 0;
+  bool terminal = false;
+  while (true) {
+    // p = softmax(target_logits[cur] / T)   (SpecTree.py:198, computed lazily for visited parents only)
+    a_load_row<CH>(target_logits + cur * ld_t, V, p);
+    {
+      float mx, sum;
+      a_stats<CH>(p, V, T, red, mx, sum);
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (i * ANT + threadIdx.x < nvec) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) p[i].h[e] = a_softmax_val(p[i].h[e], T, mx, sum);
+        }
+    }
+    const int c0 = succ_off[cur], c1 = succ_off[cur + 1];
+    if (c0 == c1) break;                                     // leaf: residual = p   (SpecTree.py:143-144)
+    a_load_row<CH>(draft_logits + cur * ld_d, V, dl);
+    int accepted = -1;
+    for (int ci = c0; ci < c1; ++ci) {
+      const int child = succ[ci];
+      const int slot = P - 1 + child;
+      const int tok = (int)tokens[slot];
+      float mx, sum;
+      a_stats<CH>(dl, V, T, red, mx, sum);                   // q = softmax(draft_logits / T)  (:149)
+      const int tc = tok >> 3, te = tok & 7;
+      if (threadIdx.x == (tc % ANT)) {
+        const int ti = tc / ANT;
+        __half ptok = f2h(0.f), dtok = f2h(0.f);
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (i == ti && e == te) { ptok = p[i].h[e]; dtok = dl[i].h[e]; }
+        const float qtok = h2f(a_softmax_val(dtok, T, mx, sum));
+        const float thr = rnd16(h2f(r[slot]) * qtok);        // r * q[token] in fp16
+        sh_flag = (h2f(ptok) > thr) ? 1 : 0;                 // strict >   (:152)
+      }
+      __syncthreads();
+      const int acc = sh_flag;
+      __syncthreads();
+      if (acc) { accepted = child; break; }
+      // p = get_residual(p, q) ; draft_logits[token] = fp16 min   (:155-156)
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (i * ANT + threadIdx.x < nvec) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float q = h2f(a_softmax_val(dl[i].h[e], T, mx, sum));
+            float d = rnd16(h2f(p[i].h[e]) - q);
+            d = (d < 0.f) ? 0.f : d;
+            p[i].h[e] = f2h(d);
+            s += d;
+          }
+        }
+      const float tot = rnd16(block_sum<ANW>(s, red));
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (i * ANT + threadIdx.x < nvec) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) p[i].h[e] = f2h(h2f(p[i].h[e]) / tot);
+        }
+      if (threadIdx.x == (tc % ANT)) {
+        const int ti = tc / ANT;
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (i == ti && e == te) dl[i].h[e] = f2h(FP16_MIN);
+      }
+    }
+    if (accepted < 0) break;                                 // residual = p   (:157)
+    const int slot = P - 1 + accepted;
+    if (threadIdx.x == 0) sh_acc[n_new] = slot;
+    ++n_new;
+    const int64_t t = tokens[slot];
+    if (t == 0 || t == 2) { terminal = true; break; }        // (:208)
+    cur = accepted;
+  }
+  __syncthreads();
+  bool nan_flag = false;
+  int64_t bonus = -1;
+  if (!terminal) {
+    int has_nan = 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (i * ANT + threadIdx.x < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) has_nan |= __hisnan(p[i].h[e]) ? 1 : 0;
+      }
+    nan_flag = __syncthreads_or(has_nan) != 0;               // torch.isnan(residual).any()  (:219)
+    if (nan_flag) {
+      terminal = true;
+    } else {
+      // residual.multinomial(1): argmax(residual / Exp(1) noise)   (:222, torch's n=1 form)
+      uint32_t best = 0u;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int c = i * ANT + threadIdx.x;
+        if (c < nvec) {
+          Pack8 nz;
+          nz.u = reinterpret_cast<const uint4*>(noise)[c];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const __half v = f2h(h2f(p[i].h[e]) / h2f(nz.h[e]));
+            best = max(best, (a_ord16(v) << 16) | (0xFFFFu - (uint32_t)(c * 8 + e)));
+          }
+        }
+      }
+      best = __reduce_max_sync(0xffffffffu, best);
+      if ((threadIdx.x & 31) == 0) redu[threadIdx.x >> 5] = best;
+      __syncthreads();
+      best = __reduce_max_sync(0xffffffffu, (threadIdx.x & 31) < ANW ? redu[threadIdx.x & 31] : 0u);
+      bonus = (int64_t)(0xFFFFu - (best & 0xFFFFu));
+    }
+  }
+  finish_verify(sh_acc, n_new, P, terminal, nan_flag, bonus, depth, S, tokens, position_ids, accept_idx, state,
+                max_target_seq);
+}
+
+__global__ void accept_greedy_kernel(const int64_t* __restrict__ target_token, const int32_t* __restrict__ succ_off,
+                                     const int32_t* __restrict__ succ, const int32_t* __restrict__ depth, int S,
+                                     int64_t* __restrict__ tokens, int64_t* __restrict__ position_ids,
+                                     int32_t* __restrict__ accept_idx, int32_t* __restrict__ state,
+                                     int max_target_seq) {
+  __shared__ int32_t sh_acc[1024];
+  __shared__ int sh_n, sh_term;
+  __shared__ long long sh_bonus;
+  const int P = state[ST_P];
+  if (threadIdx.x == 0) {
+    int cur = 0, n_new = 0, term = 0;
+    while (true) {                                           // GreedyTree.py:191-201
+      const int64_t tt = target_token[cur];
+      int acc = -1;
+      for (int ci = succ_off[cur]; ci < succ_off[cur + 1]; ++ci) {
+        const int child = succ[ci];
+        if (tokens[P - 1 + child] == tt) { acc = child; break; }
+      }
+      if (acc < 0) break;
+      const int slot = P - 1 + acc;
+      sh_acc[n_new++] = slot;
+      const int64_t t = tokens[slot];
+      if (t == 0 || t == 2) { term = 1; break; }
+      cur = acc;
+    }
+    sh_n = n_new;
+    sh_term = term;
+    sh_bonus = term ? -1 : target_token[cur];                // GreedyTree.py:207
+  }
+  __syncthreads();
+  finish_verify(sh_acc, sh_n, P, sh_term != 0, false, (int64_t)sh_bonus, depth, S, tokens, position_ids, accept_idx,
+                state, max_target_seq);
+}
+
+}  // namespace sq
+
+using namespace sq;
+
+extern "C" int sq_accept_stochastic(const sq_half* target_logits, int64_t ld_t, const sq_half* draft_logits,
+                                    int64_t ld_d, const sq_half* r, const sq_half* noise, const int32_t* succ_off,
+                                    const int32_t* succ, const int32_t* depth, int S, int V, float T, int64_t* tokens,
+                                    int64_t* position_ids, int32_t* accept_idx, int32_t* state, int max_target_seq,
+                                    void* stream) {
+  SQ_CHECK_ARG(V % 8 == 0 && V > 0 && V <= 32768, "sq_accept_stochastic: V=%d unsupported", V);
+  SQ_CHECK_ARG(S >= 1 && S <= 1024, "sq_accept_stochastic: S=%d unsupported", S);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (V <= 16384)
+    accept_stochastic_kernel<4><<<1, ANT, 0, st>>>((const __half*)target_logits, ld_t, (const __half*)draft_logits, ld_d,
+                                                  (const __half*)r, (const __half*)noise, succ_off, succ, depth, S, V, T,
+                                                  tokens, position_ids, accept_idx, state, max_target_seq);
+  else
+    accept_stochastic_kernel<8><<<1, ANT, 0, st>>>((const __half*)target_logits, ld_t, (const __half*)draft_logits, ld_d,
+                                                  (const __half*)r, (const __half*)noise, succ_off, succ, depth, S, V, T,
+                                                  tokens, position_ids, accept_idx, state, max_target_seq);
+  SQ_CHECK_LAUNCH("sq_accept_stochastic");
+  return SQ_OK;
+}
+
+extern "C" int sq_accept_greedy(const int64_t* target_token, const int32_t* succ_off, const int32_t* succ,
+                                const int32_t* depth, int S, int64_t* tokens, int64_t* position_ids,
+                                int32_t* accept_idx, int32_t* state, int max_target_seq, void* stream) {
+  SQ_CHECK_ARG(S >= 1 && S <= 1024, "sq_accept_greedy: S=%d unsupported", S);
+  accept_greedy_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(target_token, succ_off, succ, depth, S, tokens,
+                                                            position_ids, accept_idx, state, max_target_seq);
+  SQ_CHECK_LAUNCH("sq_accept_greedy");
+  return SQ_OK;
+}

@@ -1,0 +1,651 @@
+// Tree-masked attention for the draft (Engine/Llama_modules.py:127-134) and target / verify
+// (Engine/Llama_modules.py:220-248) forwards.
+//
+// Product kernel (impl 0): one CTA per (head, 128-row query tile, 128-key KV split).
+//   * Q, K and V tiles are staged in shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_128B) straight from the
+//     fused qkv activation and the static (L,1,Hkv,M,D) caches;
+//   * S = Q K^T and O = P V run on the 5th-gen tensor cores (tcgen05.mma, kind::f16, M=128) with the accumulators
+//     in tensor memory; P is written back to TMEM as the A operand of the second MMA (no shared-memory round trip);
+//   * the tree-causal mask is NOT a dense fp16 (M,M) tensor: the growmap's ancestor matrix is packed 1 bit / pair,
+//     the query tile's bit rows are staged in shared memory and combined with the device-resident prefix length;
+//     a dense additive mask (the reference API) is supported through a shared-memory tile as well;
+//   * split-KV partials (fp32 O, running max, sum) go to a workspace and a small combine kernel normalises them, so
+//     32 heads x 3 splits (config 2) or 8 heads x 6 q-tiles x 8 splits (config 4 / TP-8) fill the 148 SMs.
+// Roofline: HBM-bound for configs 2/3 (bytes = 2*D*2*(Hkv*kv + H*q) per layer), tensor-pipe-bound for config 4.
+//
+// impl 1 is a plain SIMT kernel used by the tests as an on-device cross-check of the tensor-core path.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "sq_common.cuh"
+
+struct sq_attn_plan {
+  const __half* q;
+  int ld, n_max, H, Hkv, D, L, M;
+  const __half* k_cache;
+  const __half* v_cache;
+  __half* out;
+  float* ws_o;    // [splits][H][n_pad][D]
+  float* ws_ml;   // [splits][H][n_pad][2]
+  int n_pad, splits_max;
+  int debug_flags;
+  int* err_flag;  // device word set by a watchdog timeout
+  CUtensorMap tm_q, tm_k, tm_v;
+};
+
+namespace sq {
+
+constexpr int TILE_Q = 128;
+constexpr int TILE_KV = 128;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnArgs {
+  const __half* q;
+  int ld;
+  const __half* k_layer;   // (Hkv, M, D) of this layer
+  const __half* v_layer;
+  __half* out;
+  float* ws_o;
+  float* ws_ml;
+  int n, n_pad, H, Hkv, M;
+  int layer;
+  const int32_t* state;
+  int n0, kv_end, prefix_len_host;
+  const __half* dense_mask;
+  int64_t mask_ld;
+  const uint32_t* tree_bits;
+  int tree_words, tree_size;
+  float scale;
+  int debug_flags;
+  int* err_flag;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// mask helpers (structured tree mask)
+struct RowMask {
+  int lim;          // keys c <= lim are visible (causal part)
+  int node;         // tree node id (>= 1) or -1
+};
+__device__ __forceinline__ RowMask row_mask(int slot, int P) {
+  RowMask r;
+  r.lim = min(slot, P - 1);
+  r.node = (slot >= P) ? (slot - (P - 1)) : -1;
+  return r;
+}
+// visibility bits of key columns [c0, c0+32) for one row; bits = that row's packed ancestor words (may be smem)
+__device__ __forceinline__ uint32_t vis_word(const RowMask& rm, int c0, int P, int kv_len, const uint32_t* bits,
+                                             int tree_words) {
+  uint32_t v;
+  if (rm.lim >= c0 + 31) v = 0xFFFFFFFFu;
+  else if (rm.lim < c0) v = 0u;
+  else v = (1u << (rm.lim - c0 + 1)) - 1u;
+  if (rm.node >= 0) {
+    const int j0 = c0 - (P - 1);                 // tree column of key c0
+    const int w0 = j0 >> 5;                      // arithmetic shift: floor
+    const int sh = j0 & 31;
+    const uint32_t lo = (w0 >= 0 && w0 < tree_words) ? bits[w0] : 0u;
+    const uint32_t hi = (w0 + 1 >= 0 && w0 + 1 < tree_words) ? bits[w0 + 1] : 0u;
+    v |= __funnelshift_r(lo, hi, sh);
+  }
+  const int rem = kv_len - c0;
+  if (rem <= 0) v = 0u;
+  else if (rem < 32) v &= (1u << rem) - 1u;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// impl 1: SIMT cross-check kernel.  grid (n, H), 128 threads; warp w takes keys w, w+4, ...
+template <int D>
+__global__ void __launch_bounds__(128) tree_attn_simt_kernel(AttnArgs a) {
+  constexpr int DPL = D / 32;
+  __shared__ float sh_m[4], sh_l[4];
+  __shared__ float sh_acc[4][D];
+  const int r = blockIdx.x, h = blockIdx.y;
+  const int hkv = h / (a.H / a.Hkv);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = a.state ? a.state[ST_P] : a.prefix_len_host;
+  const int base = (a.state ? (P - 1) : 0);
+  const int slot = base + a.n0 + r;
+  const int kv_len = base + a.kv_end;
+  const RowMask rm = row_mask(slot, P);
+  const uint32_t* bits = (rm.node >= 0 && a.tree_bits) ? a.tree_bits + (int64_t)rm.node * a.tree_words : nullptr;
+  float qv[DPL], acc[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) {
+    qv[i] = h2f(a.q[(int64_t)r * a.ld + h * D + lane * DPL + i]);
+    acc[i] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  const __half* kbase = a.k_layer + (int64_t)hkv * a.M * D;
+  const __half* vbase = a.v_layer + (int64_t)hkv * a.M * D;
+  for (int c = warp; c < kv_len; c += 4) {
+    float madd = 0.f;
+    if (a.dense_mask) {
+      madd = h2f(a.dense_mask[(int64_t)r * a.mask_ld + c]);
+    } else {
+      bool vis = c <= rm.lim;
+      if (!vis && bits != nullptr && c >= P - 1) {
+        const int j = c - (P - 1);
+        vis = (j < a.tree_size) && ((bits[j >> 5] >> (j & 31)) & 1u);
+      }
+      if (!vis) continue;
+    }
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) d += qv[i] * h2f(kbase[(int64_t)c * D + lane * DPL + i]);
+    d = warp_sum(d) * a.scale + madd;
+    const float mn = fmaxf(m, d);
+    const float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
+    const float p = expf(d - mn);
+    l = l * corr + p;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[i] = acc[i] * corr + p * h2f(vbase[(int64_t)c * D + lane * DPL + i]);
+    m = mn;
+  }
+  if (lane == 0) { sh_m[warp] = m; sh_l[warp] = l; }
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) sh_acc[warp][lane * DPL + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float mm = fmaxf(fmaxf(sh_m[0], sh_m[1]), fmaxf(sh_m[2], sh_m[3]));
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      if (sh_m[w] == -INFINITY) continue;
+      const float f = expf(sh_m[w] - mm);
+      num += f * sh_acc[w][threadIdx.x];
+      den += f * sh_l[w];
+    }
+    a.out[(int64_t)r * (a.H * D) + h * D + threadIdx.x] = f2h(den > 0.f ? num / den : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a descriptor / protocol bug must never hang the GPU (the box is shared); on timeout flag + continue
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  const long long t0 = clock64();
+  bool ok = false;
+  while (!(ok = mbar_try_wait(bar, parity))) {
+    if (clock64() - t0 > 2000000000LL) break;    // ~1 s
+  }
+  if (!ok && err_flag) atomicExch(err_flag, code);
+  __syncwarp();
+  return ok;
+}
+// single-thread variant (called under `if (tid == 0)`): no warp re-convergence inside
+__device__ __forceinline__ bool mbar_wait_one(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  const long long t0 = clock64();
+  bool ok = false;
+  while (!(ok = mbar_try_wait(bar, parity))) {
+    if (clock64() - t0 > 2000000000LL) break;
+  }
+  if (!ok && err_flag) atomicExch(err_flag, code);
+  return ok;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+}  // namespace ptx
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
+  d |= (uint64_t)2 << 61;   // layout_type = SWIZZLE_128B
+  return d;
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): f16 x f16 -> f32, M=128
+__host__ __device__ constexpr uint32_t umma_idesc(int n, bool b_mn_major) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(TILE_Q >> 4) << 24);
+}
+
+template <int D>
+struct TcSmem {
+  static constexpr int HALVES = D / 64;                 // 64-element (128 B) column halves
+  static constexpr int TILE_BYTES = HALVES * 128 * 128; // one 128-row tile
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = TILE_BYTES;
+  static constexpr int OFF_V = 2 * TILE_BYTES;
+  static constexpr int OFF_MASK = 3 * TILE_BYTES;       // 128 x 132 halfs (dense) or 128 x tree_words u32 (bits)
+  static constexpr int MASK_BYTES = 128 * 132 * 2;
+  static constexpr int OFF_BAR = OFF_MASK + MASK_BYTES; // 3 mbarriers + tmem ptr
+  static constexpr int TOTAL = OFF_BAR + 64;
+};
+
+// impl 0: grid (H, q_tiles, kv_splits), 128 threads.
+template <int D>
+__global__ void __launch_bounds__(128, 1)
+    tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, AttnArgs a) {
+  using SM = TcSmem<D>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16 B aligned: re-align to 1024 B for SWIZZLE_128B
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int h = blockIdx.x, qt = blockIdx.y, split = blockIdx.z;
+  const int hkv = h / (a.H / a.Hkv);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int P = a.state ? a.state[ST_P] : a.prefix_len_host;
+  const int base = a.state ? (P - 1) : 0;
+  const int kv_len = base + a.kv_end;
+  const int kv0 = split * TILE_KV;
+  const int q0 = qt * TILE_Q;
+  const int row = q0 + tid;                      // this thread's query row (TMEM lane tid)
+  const int slot = base + a.n0 + row;
+  float* ws_ml = a.ws_ml + (((int64_t)split * a.H + h) * a.n_pad + row) * 2;
+  float* ws_o = a.ws_o + (((int64_t)split * a.H + h) * a.n_pad + row) * D;
+
+  if (kv0 >= kv_len) return;                     // inactive split (combine only reads ceil(kv_len/128) splits)
+  // whole tile masked for every row of this q tile?  (structured mode only)
+  if (!a.dense_mask) {
+    const int last_slot = base + a.n0 + min(q0 + TILE_Q, a.n) - 1;
+    const int max_vis = (last_slot >= P) ? (kv_len - 1) : min(last_slot, P - 1);
+    if (kv0 > max_vis) {
+      if (row < a.n) { ws_ml[0] = -INFINITY; ws_ml[1] = 0.f; }
+      return;
+    }
+  }
+
+  const uint32_t sQ = ptx::smem_u32(smem + SM::OFF_Q), sK = ptx::smem_u32(smem + SM::OFF_K),
+                 sV = ptx::smem_u32(smem + SM::OFF_V);
+  const uint32_t bar_qk = ptx::smem_u32(smem + SM::OFF_BAR), bar_v = bar_qk + 8, bar_mma = bar_qk + 16;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + 32);
+
+  if (tid == 0) {
+    ptx::mbar_init(bar_qk, 1);
+    ptx::mbar_init(bar_v, 1);
+    ptx::mbar_init(bar_mma, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  const uint32_t tm_S = tmem;                    // 128 fp32 columns
+  const uint32_t tm_P = tmem;                    // 64 columns (fp16 pairs), aliases S
+  const uint32_t tm_O = tmem + 128;              // D fp32 columns
+
+  if (tid == 0) {
+    ptx::mbar_expect_tx(bar_qk, 2 * SM::TILE_BYTES);
+    ptx::mbar_expect_tx(bar_v, SM::TILE_BYTES);
+#pragma unroll
+    for (int hh = 0; hh < SM::HALVES; ++hh) {
+      ptx::tma_load_2d(sQ + hh * 16384, &tm_q, bar_qk, h * D + hh * 64, q0);
+      ptx::tma_load_3d(sK + hh * 16384, &tm_k, bar_qk, hh * 64, kv0, a.layer * a.Hkv + hkv);
+    }
+#pragma unroll
+    for (int hh = 0; hh < SM::HALVES; ++hh)
+      ptx::tma_load_3d(sV + hh * 16384, &tm_v, bar_v, hh * 64, kv0, a.layer * a.Hkv + hkv);
+  }
+
+  // stage the mask of this (q tile, kv tile) in shared memory while the TMA loads fly
+  const RowMask rm = row_mask(slot, P);
+  uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + SM::OFF_MASK);
+  __half* smask = reinterpret_cast<__half*>(smem + SM::OFF_MASK);
+  if (a.dense_mask) {
+    for (int i = tid; i < TILE_Q * TILE_KV; i += 128) {
+      const int rr = i / TILE_KV, cc = i % TILE_KV;
+      __half v = __float2half(0.f);
+      if (q0 + rr < a.n && kv0 + cc < kv_len) v = a.dense_mask[(int64_t)(q0 + rr) * a.mask_ld + kv0 + cc];
+      smask[rr * 132 + cc] = v;
+    }
+  } else if (a.tree_bits) {
+    for (int i = tid; i < TILE_Q * a.tree_words; i += 128) {
+      const int rr = i / a.tree_words, w = i % a.tree_words;
+      const int node = base + a.n0 + q0 + rr - (P - 1);
+      sbits[i] = (node >= 1 && node < a.tree_size) ? a.tree_bits[(int64_t)node * a.tree_words + w] : 0u;
+    }
+  }
+  __syncthreads();
+
+  // ---- S = Q K^T --------------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    ptx::mbar_wait_one(bar_qk, 0, a.err_flag, 1);
+    ptx::tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc(TILE_KV, false);
+#pragma unroll
+    for (int k = 0; k < D / 16; ++k) {
+      const uint32_t off = (k / 4) * 16384 + (k % 4) * 32;          // 4 k-steps per 128 B swizzle atom
+      ptx::mma_ss(tm_S, umma_desc(sQ + off, 16, 1024), umma_desc(sK + off, 16, 1024), idesc, k > 0);
+    }
+    ptx::tc_commit(bar_mma);
+  }
+  ptx::mbar_wait(bar_mma, 0, a.err_flag, 2);
+  ptx::tc_fence_after();
+
+  // ---- softmax over this tile (thread == row, TMEM lane == row) ---------------------------------------------------
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const float sc = a.scale * LOG2E;              // work in the log2 domain
+  const uint32_t* my_bits = sbits + tid * a.tree_words;
+  float mx = -INFINITY;
+  uint32_t vis[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t r[32];
+    ptx::tmem_ld32(tm_S + lane_base + j * 32, r);
+    if (a.dense_mask) {
+      const int rem = kv_len - (kv0 + j * 32);
+      vis[j] = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if ((vis[j] >> e) & 1u)
+          mx = fmaxf(mx, __uint_as_float(r[e]) * sc + h2f(smask[tid * 132 + j * 32 + e]) * LOG2E);
+    } else {
+      vis[j] = vis_word(rm, kv0 + j * 32, P, kv_len, my_bits, a.tree_words);
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if ((vis[j] >> e) & 1u) mx = fmaxf(mx, __uint_as_float(r[e]) * sc);
+    }
+  }
+  float lsum = 0.f;
+  const float mref = (mx == -INFINITY) ? 0.f : mx;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t r[32];
+    ptx::tmem_ld32(tm_S + lane_base + j * 32, r);
+    uint32_t pk[16];
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      float p0 = 0.f, p1 = 0.f;
+      if ((vis[j] >> e) & 1u) {
+        float s = __uint_as_float(r[e]) * sc;
+        if (a.dense_mask) s += h2f(smask[tid * 132 + j * 32 + e]) * LOG2E;
+        p0 = exp2f(s - mref);
+      }
+      if ((vis[j] >> (e + 1)) & 1u) {
+        float s = __uint_as_float(r[e + 1]) * sc;
+        if (a.dense_mask) s += h2f(smask[tid * 132 + j * 32 + e + 1]) * LOG2E;
+        p1 = exp2f(s - mref);
+      }
+      const __half2 hp = __floats2half2_rn(p0, p1);           // P is fp16 like the reference's attn_weights
+      lsum += __low2float(hp) + __high2float(hp);
+      pk[e / 2] = *reinterpret_cast<const uint32_t*>(&hp);
+    }
+    ptx::tmem_st16(tm_P + lane_base + j * 16, pk);
+  }
+  ptx::tmem_st_wait();
+  ptx::tc_fence_before();
+  __syncthreads();
+
+  // ---- O = P V ----------------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    ptx::tc_fence_after();
+    ptx::mbar_wait_one(bar_v, 0, a.err_flag, 3);
+    ptx::tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc(D, true);
+    const uint32_t lbo = (a.debug_flags & 1) ? 1024u : 16384u;   // stride between 64-wide D halves
+    const uint32_t sbo = (a.debug_flags & 1) ? 16384u : 1024u;   // stride between 8-key groups
+#pragma unroll
+    for (int k = 0; k < TILE_KV / 16; ++k)
+      ptx::mma_ts(tm_O, tm_P + k * 8, umma_desc(sV + k * 2048, lbo, sbo), idesc, k > 0);
+    ptx::tc_commit(bar_mma);
+  }
+  ptx::mbar_wait(bar_mma, 1, a.err_flag, 4);
+  ptx::tc_fence_after();
+
+  if (row < a.n) {
+    ws_ml[0] = mx;       // log2-domain running max
+    ws_ml[1] = lsum;
+  }
+#pragma unroll
+  for (int j = 0; j < D / 32; ++j) {
+    uint32_t r[32];
+    ptx::tmem_ld32(tm_O + lane_base + j * 32, r);
+    if (row < a.n) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 4)
+        *reinterpret_cast<uint4*>(ws_o + j * 32 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
+// combine split-KV partials: grid (n, H), D threads
+template <int D>
+__global__ void __launch_bounds__(D) tree_attn_combine_kernel(AttnArgs a) {
+  const int r = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+  const int P = a.state ? a.state[ST_P] : a.prefix_len_host;
+  const int kv_len = (a.state ? (P - 1) : 0) + a.kv_end;
+  const int nsplit = (kv_len + TILE_KV - 1) / TILE_KV;
+  float mm = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, a.ws_ml[(((int64_t)s * a.H + h) * a.n_pad + r) * 2]);
+  float num = 0.f, den = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const int64_t o = ((int64_t)s * a.H + h) * a.n_pad + r;
+    const float m = a.ws_ml[o * 2];
+    if (m == -INFINITY) continue;
+    const float f = exp2f(m - mm);
+    num += f * a.ws_o[o * D + d];
+    den += f * a.ws_ml[o * 2 + 1];
+  }
+  a.out[(int64_t)r * (a.H * D) + h * D + d] = f2h(den > 0.f ? num / den : 0.f);
+}
+
+}  // namespace sq
+
+using namespace sq;
+
+// ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return SQ_ERR_CUDA; }
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return SQ_ERR_CUDA; }
+  return SQ_OK;
+}
+
+extern "C" int64_t sq_attn_workspace_bytes(int n_max, int H, int D, int M) {
+  const int64_t n_pad = ((n_max + TILE_Q - 1) / TILE_Q) * TILE_Q;
+  const int64_t splits = (M + TILE_KV - 1) / TILE_KV;
+  return splits * H * n_pad * (D + 2) * 4 + 256;
+}
+
+extern "C" int sq_attn_plan_create(sq_attn_plan** plan, const sq_half* q, int ld, int n_max, int H, int Hkv, int D,
+                                   const sq_half* k_cache, const sq_half* v_cache, int L, int M, sq_half* out,
+                                   void* workspace, int64_t workspace_bytes) {
+  SQ_CHECK_ARG(plan != nullptr, "sq_attn_plan_create: null plan");
+  SQ_CHECK_ARG(D == 64 || D == 128, "sq_attn_plan_create: head_dim %d unsupported (64 or 128)", D);
+  SQ_CHECK_ARG(H % Hkv == 0 && ld % 8 == 0 && n_max >= 1, "sq_attn_plan_create: bad shape");
+  SQ_CHECK_ARG(workspace_bytes >= sq_attn_workspace_bytes(n_max, H, D, M), "sq_attn_plan_create: workspace too small");
+  SQ_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k_cache % 16 == 0) && ((uintptr_t)v_cache % 16 == 0),
+               "sq_attn_plan_create: pointers must be 16 B aligned");
+  sq_attn_plan* p = new sq_attn_plan();
+  p->q = (const __half*)q; p->ld = ld; p->n_max = n_max; p->H = H; p->Hkv = Hkv; p->D = D; p->L = L; p->M = M;
+  p->k_cache = (const __half*)k_cache; p->v_cache = (const __half*)v_cache; p->out = (__half*)out;
+  p->n_pad = ((n_max + TILE_Q - 1) / TILE_Q) * TILE_Q;
+  p->splits_max = (M + TILE_KV - 1) / TILE_KV;
+  p->ws_o = (float*)workspace;
+  p->ws_ml = p->ws_o + (int64_t)p->splits_max * H * p->n_pad * D;
+  p->err_flag = (int*)(p->ws_ml + (int64_t)p->splits_max * H * p->n_pad * 2);
+  const char* dbg = getenv("SQ_ATTN_DEBUG");
+  p->debug_flags = dbg ? atoi(dbg) : 0;
+  cudaMemset(p->err_flag, 0, sizeof(int));
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)n_max};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)TILE_Q};
+    int rc = encode_map(&p->tm_q, q, 2, dims, strides, box);
+    if (rc) { delete p; return rc; }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)M, (cuuint64_t)L * Hkv};
+    cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)M * D * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)TILE_KV, 1};
+    int rc = encode_map(&p->tm_k, k_cache, 3, dims, strides, box);
+    if (!rc) rc = encode_map(&p->tm_v, v_cache, 3, dims, strides, box);
+    if (rc) { delete p; return rc; }
+  }
+  *plan = p;
+  return SQ_OK;
+}
+
+extern "C" int sq_attn_plan_destroy(sq_attn_plan* plan) {
+  delete plan;
+  return SQ_OK;
+}
+
+extern "C" int sq_attn_plan_error(sq_attn_plan* plan) {
+  int v = 0;
+  cudaMemcpy(&v, plan->err_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  return v;
+}
+
+template <int D>
+static int launch_attn(sq_attn_plan* p, AttnArgs& a, int impl, cudaStream_t st) {
+  if (impl == 1) {
+    tree_attn_simt_kernel<D><<<dim3(a.n, a.H), 128, 0, st>>>(a);
+    SQ_CHECK_LAUNCH("sq_tree_attn(simt)");
+    return SQ_OK;
+  }
+  static bool attr_set = false;
+  constexpr int smem = TcSmem<D>::TOTAL + 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tree_attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("sq_tree_attn: smem attr: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int q_tiles = (a.n + TILE_Q - 1) / TILE_Q;
+  tree_attn_tc_kernel<D><<<dim3(a.H, q_tiles, p->splits_max), 128, smem, st>>>(p->tm_q, p->tm_k, p->tm_v, a);
+  SQ_CHECK_LAUNCH("sq_tree_attn(tc)");
+  tree_attn_combine_kernel<D><<<dim3(a.n, a.H), D, 0, st>>>(a);
+  SQ_CHECK_LAUNCH("sq_tree_attn(combine)");
+  return SQ_OK;
+}
+
+extern "C" int sq_tree_attn(sq_attn_plan* plan, int layer, int n, const int32_t* state, int n0, int kv_end,
+                            int prefix_len_host, const sq_half* dense_mask, int64_t mask_ld, const uint32_t* tree_bits,
+                            int tree_words, int tree_size, int impl, void* stream) {
+  SQ_CHECK_ARG(plan != nullptr, "sq_tree_attn: null plan");
+  SQ_CHECK_ARG(n >= 0 && n <= plan->n_max, "sq_tree_attn: n=%d exceeds plan n_max=%d", n, plan->n_max);
+  SQ_CHECK_ARG(layer >= 0 && layer < plan->L, "sq_tree_attn: bad layer %d", layer);
+  SQ_CHECK_ARG(tree_words <= 32, "sq_tree_attn: tree_size > 1024 unsupported");
+  SQ_CHECK_ARG(state != nullptr || kv_end <= plan->M, "sq_tree_attn: kv_end %d > M %d", kv_end, plan->M);
+  if (n == 0) return SQ_OK;
+  AttnArgs a;
+  a.q = plan->q; a.ld = plan->ld;
+  a.k_layer = plan->k_cache + (int64_t)layer * plan->Hkv * plan->M * plan->D;
+  a.v_layer = plan->v_cache + (int64_t)layer * plan->Hkv * plan->M * plan->D;
+  a.out = plan->out; a.ws_o = plan->ws_o; a.ws_ml = plan->ws_ml;
+  a.n = n; a.n_pad = plan->n_pad; a.H = plan->H; a.Hkv = plan->Hkv; a.M = plan->M; a.layer = layer;
+  a.state = state; a.n0 = n0; a.kv_end = kv_end; a.prefix_len_host = prefix_len_host;
+  a.dense_mask = (const __half*)dense_mask; a.mask_ld = mask_ld;
+  a.tree_bits = tree_bits; a.tree_words = tree_bits ? tree_words : 0; a.tree_size = tree_bits ? tree_size : 0;
+  a.scale = 1.0f / sqrtf((float)plan->D);
+  a.debug_flags = plan->debug_flags; a.err_flag = plan->err_flag;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->D == 64) return launch_attn<64>(plan, a, impl, st);
+  return launch_attn<128>(plan, a, impl, st);
+}

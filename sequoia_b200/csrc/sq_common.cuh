@@ -1,0 +1,95 @@
+// Shared helpers for the sequoia_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sequoia_b200.h"
+
+namespace sq {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n);
+
+#define SQ_CHECK_ARG(cond, ...)                     \
+  do {                                              \
+    if (!(cond)) {                                  \
+      sq::set_error(__VA_ARGS__);                   \
+      return SQ_ERR_INVALID_ARG;                    \
+    }                                               \
+  } while (0)
+
+#define SQ_CHECK_LAUNCH(name)                                                   \
+  do {                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                       \
+    if (e__ != cudaSuccess) {                                                   \
+      sq::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \
+      return SQ_ERR_CUDA;                                                       \
+    }                                                                           \
+    sq::count_launch(1);                                                        \
+  } while (0)
+
+// Device-side decode state (int32 words), owned by the Tree object, read by every kernel
+// that needs the dynamic prefix length so that whole iterations are CUDA-graph static.
+enum StateWord : int {
+  ST_P = 0,          // ground_truth_len: committed tokens incl. the root (bonus) token
+  ST_ACCEPT_LEN = 1, // a = len(accept_list) of the last verify
+  ST_TERMINAL = 2,   // 1 if the last verify hit EOS/pad or a NaN residual
+  ST_N_NEW = 3,      // number of tree nodes accepted by the last verify (a - P_old)
+  ST_P_OLD = 4,      // ground_truth_len the last verify started from
+  ST_BONUS = 5,      // bonus token (-1 when terminal)
+  ST_NAN = 6,        // residual had a NaN
+  ST_SKIPPED = 7,    // prepare_for_next_iter was skipped (a + 1 > max_target_seq)
+  ST_WORDS = 16
+};
+
+__device__ __forceinline__ int row_base(const int32_t* P_ptr, int n0) {
+  return (P_ptr ? (P_ptr[ST_P] - 1) : 0) + n0;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide reductions for blockDim.x = 32 * NW threads; `red` is NW floats of shared memory.
+// The result is identical in every thread (fixed combination order => deterministic).
+template <int NW>
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float r = (l < NW) ? red[l] : -INFINITY;
+  return warp_max(r);
+}
+template <int NW>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float r = (l < NW) ? red[l] : 0.f;
+  return warp_sum(r);
+}
+
+// fp16 helpers that reproduce torch's "compute in fp32, round to fp16" element-wise semantics.
+__device__ __forceinline__ float h2f(__half h) { return __half2float(h); }
+__device__ __forceinline__ __half f2h(float f) { return __float2half_rn(f); }
+__device__ __forceinline__ float rnd16(float f) { return __half2float(__float2half_rn(f)); }
+
+union Pack8 {
+  uint4 u;
+  __half h[8];
+  __half2 h2[4];
+};
+
+}  // namespace sq

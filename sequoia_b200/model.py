@@ -1,0 +1,250 @@
+"""Tree-masked Llama forward on the sequoia_b200 kernels.
+
+Replaces Engine/Llama_model.py + Engine/Llama_modules.py of the reference (LlamaForCausalLM_FI / _TG):
+embed -> L x [RMSNorm, fused QKV GEMM, RoPE + KV append, tree attention, o_proj, residual+RMSNorm,
+fused gate/up GEMM, SiLU*up, down_proj, residual+RMSNorm] -> lm_head.
+
+* the dense weight GEMMs stay on cuBLASLt through torch.mm (not a hand-written
+  kernel on this path); everything else is a launch into libsequoia_b200.so;
+* q/k/v and gate/up weights are concatenated at load time so one GEMM feeds each fused kernel;
+* every buffer is preallocated for n_max rows, so a forward allocates nothing and is CUDA-graph
+  capturable; dynamic quantities (prefix length, kv length) are read from the device state word;
+* optional tensor parallelism (Megatron layout): column-parallel qkv / gate_up, row-parallel
+  o_proj / down_proj followed by an NCCL sum-allreduce (2 per layer), KV cache sharded by kv head.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+F16 = torch.float16
+
+
+@dataclass
+class LlamaConfigLite:
+    hidden_size: int
+    intermediate_size: int
+    num_hidden_layers: int
+    num_attention_heads: int
+    num_key_value_heads: int
+    vocab_size: int = 32000
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 10000.0
+    max_position_embeddings: int = 2048
+
+    @property
+    def head_dim(self):
+        return self.hidden_size // self.num_attention_heads
+
+
+# public HF configs of the model sizes BASELINE.json names (random-init weights of these shapes)
+NAMED_CONFIGS = {
+    "llama-68m": LlamaConfigLite(768, 3072, 2, 12, 12),
+    "llama-160m": LlamaConfigLite(768, 3072, 12, 12, 12),
+    "llama-2-7b": LlamaConfigLite(4096, 11008, 32, 32, 32, rms_norm_eps=1e-5, max_position_embeddings=4096),
+    "llama-2-13b": LlamaConfigLite(5120, 13824, 40, 40, 40, rms_norm_eps=1e-5, max_position_embeddings=4096),
+    "llama-2-70b": LlamaConfigLite(8192, 28672, 80, 64, 8, rms_norm_eps=1e-5, max_position_embeddings=4096),
+}
+
+
+def config_from(obj) -> LlamaConfigLite:
+    if isinstance(obj, LlamaConfigLite):
+        return obj
+    g = (lambda k, d=None: obj.get(k, d)) if isinstance(obj, dict) else (lambda k, d=None: getattr(obj, k, d))
+    theta = g("rope_theta", None)
+    return LlamaConfigLite(
+        hidden_size=g("hidden_size"), intermediate_size=g("intermediate_size"),
+        num_hidden_layers=g("num_hidden_layers"), num_attention_heads=g("num_attention_heads"),
+        num_key_value_heads=g("num_key_value_heads") or g("num_attention_heads"), vocab_size=g("vocab_size", 32000),
+        rms_norm_eps=g("rms_norm_eps", 1e-6), rope_theta=float(theta) if theta else 10000.0,
+        max_position_embeddings=g("max_position_embeddings", 2048))
+
+
+def _load_state_dict_dir(path: str) -> Dict[str, torch.Tensor]:
+    sd: Dict[str, torch.Tensor] = {}
+    files = sorted(os.listdir(path))
+    st = [f for f in files if f.endswith(".safetensors")]
+    if st:
+        from safetensors.torch import load_file
+        for f in st:
+            sd.update(load_file(os.path.join(path, f)))
+        return sd
+    for f in files:
+        if f.endswith(".bin") or f.endswith(".pt"):
+            sd.update(torch.load(os.path.join(path, f), map_location="cpu"))
+    if not sd:
+        raise FileNotFoundError(f"no weight files (*.safetensors / *.bin) in {path}")
+    return sd
+
+
+class _RandomInit:
+    """HF-default random init (normal std 0.02, norms = 1) generated on the device, tensor by tensor, from a seeded
+    generator; the FULL tensor is always drawn and then sharded, so every TP degree sees the same model."""
+
+    def __init__(self, cfg: LlamaConfigLite, seed: int, device):
+        self.cfg, self.device = cfg, device
+        self.g = torch.Generator(device=device)
+        self.g.manual_seed(seed)
+
+    def get(self, name: str, shape) -> torch.Tensor:
+        if name.endswith("norm.weight") or "layernorm" in name:
+            return torch.ones(shape, dtype=F16, device=self.device)
+        t = torch.empty(shape, dtype=F16, device=self.device)
+        t.normal_(0.0, 0.02, generator=self.g)
+        return t
+
+
+class _DictSource:
+    def __init__(self, sd: Dict[str, torch.Tensor], device):
+        self.sd, self.device = sd, device
+
+    def get(self, name: str, shape) -> torch.Tensor:
+        t = self.sd[name]
+        assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
+        return t.to(device=self.device, dtype=F16)
+
+
+def resolve_model(model_name_or_path, device):
+    """-> (LlamaConfigLite, weight source).  Accepted forms of `model_name_or_path`:
+       * directory with config.json + *.safetensors / *.bin   (what from_pretrained took, Engine/Engine.py:18)
+       * "random-init:<name>[:seed]" with <name> in NAMED_CONFIGS   (synthetic benchmarks, no network)
+       * {"config": cfg, "state_dict": {...}}   (tests: weights shared with the oracle)."""
+    if isinstance(model_name_or_path, dict):
+        cfg = config_from(model_name_or_path["config"])
+        return cfg, _DictSource(model_name_or_path["state_dict"], device)
+    s = str(model_name_or_path)
+    if s.startswith("random-init:"):
+        parts = s.split(":")
+        cfg = NAMED_CONFIGS[parts[1].lower()]
+        seed = int(parts[2]) if len(parts) > 2 else 0
+        return cfg, _RandomInit(cfg, seed, device)
+    if os.path.isdir(s):
+        with open(os.path.join(s, "config.json")) as f:
+            cfg = config_from(json.load(f))
+        return cfg, _DictSource(_load_state_dict_dir(s), device)
+    raise FileNotFoundError(
+        f"{s!r}: expected a local model directory or 'random-init:<{'|'.join(NAMED_CONFIGS)}>[:seed]' "
+        "(there is no network access for hub downloads)")
+
+
+def rope_cache(cfg: LlamaConfigLite, max_length: int, device):
+    """LlamaRotaryEmbedding_FI (Engine/Llama_modules.py:16-45): fp32 tables, sliced [:max_length], cast to fp16."""
+    d = cfg.head_dim
+    inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    t = torch.arange(cfg.max_position_embeddings, dtype=torch.float32)
+    freqs = torch.outer(t, inv_freq)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return (emb.cos()[:max_length].to(F16).to(device).contiguous(), emb.sin()[:max_length].to(F16).to(device).contiguous())
+
+
+class TPInfo:
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.group = group
+        if group is None:
+            self.rank, self.size = 0, 1
+        else:
+            self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_reduce(self, t: torch.Tensor):
+        if self.size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.group)
+
+
+class LlamaRunner:
+    """Weights + preallocated activations + attention plan of one engine."""
+
+    def __init__(self, model_name_or_path, max_length: int, device="cuda:0", tp_group=None, n_max: Optional[int] = None):
+        self.device = torch.device(device)
+        self.cfg, src = resolve_model(model_name_or_path, self.device)
+        cfg = self.cfg
+        self.tp = TPInfo(tp_group)
+        tp, r = self.tp.size, self.tp.rank
+        assert cfg.num_attention_heads % tp == 0 and cfg.num_key_value_heads % tp == 0 and cfg.intermediate_size % tp == 0
+        self.M = max_length
+        self.n_max = n_max or max_length
+        self.H, self.Hkv, self.D = cfg.num_attention_heads // tp, cfg.num_key_value_heads // tp, cfg.head_dim
+        self.I = cfg.intermediate_size // tp
+        h, D, V = cfg.hidden_size, self.D, cfg.vocab_size
+        self.h, self.V, self.L = h, V, cfg.num_hidden_layers
+        Hf, Hkvf, If = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.intermediate_size
+        self.embed = src.get("model.embed_tokens.weight", (V, h))
+        self.layers = []
+        for l in range(self.L):
+            p = f"model.layers.{l}."
+            wq = src.get(p + "self_attn.q_proj.weight", (Hf * D, h))[r * self.H * D:(r + 1) * self.H * D]
+            wk = src.get(p + "self_attn.k_proj.weight", (Hkvf * D, h))[r * self.Hkv * D:(r + 1) * self.Hkv * D]
+            wv = src.get(p + "self_attn.v_proj.weight", (Hkvf * D, h))[r * self.Hkv * D:(r + 1) * self.Hkv * D]
+            wo = src.get(p + "self_attn.o_proj.weight", (h, Hf * D))[:, r * self.H * D:(r + 1) * self.H * D]
+            wg = src.get(p + "mlp.gate_proj.weight", (If, h))[r * self.I:(r + 1) * self.I]
+            wu = src.get(p + "mlp.up_proj.weight", (If, h))[r * self.I:(r + 1) * self.I]
+            wd = src.get(p + "mlp.down_proj.weight", (h, If))[:, r * self.I:(r + 1) * self.I]
+            self.layers.append(dict(
+                wqkv=torch.cat([wq, wk, wv], dim=0).contiguous(), wo=wo.contiguous(),
+                wgu=torch.cat([wg, wu], dim=0).contiguous(), wd=wd.contiguous(),
+                ln1=src.get(p + "input_layernorm.weight", (h,)), ln2=src.get(p + "post_attention_layernorm.weight", (h,))))
+            del wq, wk, wv, wo, wg, wu, wd
+        self.norm = src.get("model.norm.weight", (h,))
+        self.lm_head = src.get("lm_head.weight", (V, h))
+        self.cos, self.sin = rope_cache(cfg, max_length, self.device)
+        self.eps = float(cfg.rms_norm_eps)
+        n = self.n_max
+        dev = self.device
+        z = lambda *s: torch.zeros(*s, dtype=F16, device=dev)
+        self.hidden, self.normed = z(n, h), z(n, h)
+        self.qkv = z(n, (self.H + 2 * self.Hkv) * D)
+        self.attn_out, self.proj = z(n, self.H * D), z(n, h)
+        self.gate_up, self.act = z(n, 2 * self.I), z(n, self.I)
+        self.logits = z(n, V)
+        self.k_cache = torch.zeros(self.L, 1, self.Hkv, max_length, D, dtype=F16, device=dev)
+        self.v_cache = torch.zeros_like(self.k_cache)
+        self.plan = ops.AttnPlan(self.qkv, n, self.H, self.Hkv, D, self.k_cache, self.v_cache, self.attn_out)
+        self.attn_impl = int(os.environ.get("SQ_ATTN_IMPL", "0"))
+
+    def weight_bytes(self) -> int:
+        b = self.embed.numel() + self.lm_head.numel() + self.norm.numel()
+        for ly in self.layers:
+            b += sum(ly[k].numel() for k in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2"))
+        return 2 * b
+
+    @torch.no_grad()
+    def forward(self, n: int, tokens: torch.Tensor, position_ids: torch.Tensor, storage_ids: torch.Tensor, *,
+                state=None, n0: int = 0, kv_end: int = 0, prefix_len: int = 0, dense_mask=None, mask_ld: int = 0,
+                tree_bits=None, tree_words: int = 0, tree_size: int = 0, logits_out: Optional[torch.Tensor] = None,
+                logits_from: int = 0) -> torch.Tensor:
+        """Forward `n` rows.  Row r is token tokens[base+r] at position position_ids[base+r], written to cache slot
+        storage_ids[base+r], base = (state ? P-1 : 0) + n0.  Attends slots [0, (state ? P-1 : 0) + kv_end).
+        Logits of rows [logits_from, n) are written to `logits_out` (default: the internal buffer) and returned."""
+        assert 0 < n <= self.n_max
+        H, Hkv, D, M = self.H, self.Hkv, self.D, self.M
+        hid, nrm = self.hidden[:n], self.normed[:n]
+        ops.embed_rows(self.embed, tokens, n, self.hidden, state=state, n0=n0)
+        ops.rmsnorm(self.hidden, self.layers[0]["ln1"], self.normed, n, self.eps)
+        for l, ly in enumerate(self.layers):
+            torch.mm(nrm, ly["wqkv"].t(), out=self.qkv[:n])
+            ops.rope_kv_append(self.qkv, H, Hkv, D, self.cos, self.sin, position_ids, storage_ids, n,
+                               self.k_cache[l], self.v_cache[l], M, state=state, n0=n0)
+            ops.tree_attn(self.plan, l, n, state=state, n0=n0, kv_end=kv_end, prefix_len=prefix_len,
+                          dense_mask=dense_mask, mask_ld=mask_ld, tree_bits=tree_bits, tree_words=tree_words,
+                          tree_size=tree_size, impl=self.attn_impl)
+            torch.mm(self.attn_out[:n], ly["wo"].t(), out=self.proj[:n])
+            self.tp.all_reduce(self.proj[:n])
+            ops.add_rmsnorm(self.hidden, self.proj, ly["ln2"], self.normed, n, self.eps)
+            torch.mm(nrm, ly["wgu"].t(), out=self.gate_up[:n])
+            ops.silu_mul(self.gate_up, self.act, n)
+            torch.mm(self.act[:n], ly["wd"].t(), out=self.proj[:n])
+            self.tp.all_reduce(self.proj[:n])
+            nxt = self.layers[l + 1]["ln1"] if l + 1 < self.L else self.norm
+            ops.add_rmsnorm(self.hidden, self.proj, nxt, self.normed, n, self.eps)
+        m = n - logits_from
+        out = logits_out if logits_out is not None else self.logits[:m]
+        torch.mm(self.normed[logits_from:n], self.lm_head.t(), out=out)
+        return out

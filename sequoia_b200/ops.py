@@ -1,0 +1,144 @@
+"""Tensor-level wrappers over the C ABI (one function per exported kernel).
+
+Everything here launches on torch's current CUDA stream, never allocates on the hot path unless
+an output tensor is not supplied, and raises on any error (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+F16 = torch.float16
+
+
+def _need(t: torch.Tensor, dtype, name: str):
+    if t.dtype != dtype or not t.is_cuda:
+        raise TypeError(f"{name}: expected CUDA tensor of {dtype}, got {t.dtype} on {t.device}")
+
+
+def embed_rows(table, tokens, n, out, state=None, n0=0):
+    lib = _lib.load()
+    check(lib.sq_embed_rows(ptr(table), ptr(tokens), ptr(state), n0, n, table.shape[1], ptr(out), stream_ptr()),
+          "sq_embed_rows")
+
+
+def rmsnorm(x, weight, out, n, eps):
+    lib = _lib.load()
+    check(lib.sq_rmsnorm(ptr(x), ptr(weight), ptr(out), n, x.shape[-1], eps, stream_ptr()), "sq_rmsnorm")
+
+
+def add_rmsnorm(resid, delta, weight, out, n, eps):
+    lib = _lib.load()
+    check(lib.sq_add_rmsnorm(ptr(resid), ptr(delta), ptr(weight), ptr(out), n, resid.shape[-1], eps, stream_ptr()),
+          "sq_add_rmsnorm")
+
+
+def silu_mul(gate_up, out, n):
+    lib = _lib.load()
+    check(lib.sq_silu_mul(ptr(gate_up), ptr(out), n, out.shape[-1], stream_ptr()), "sq_silu_mul")
+
+
+def rope_kv_append(qkv, H, Hkv, D, cos, sin, position_ids, storage_ids, n, k_layer, v_layer, M, state=None, n0=0):
+    lib = _lib.load()
+    check(lib.sq_rope_kv_append(ptr(qkv), qkv.shape[-1], H, Hkv, D, ptr(cos), ptr(sin), ptr(position_ids),
+                                ptr(storage_ids), ptr(state), n0, n, ptr(k_layer), ptr(v_layer), M, stream_ptr()),
+          "sq_rope_kv_append")
+
+
+def kv_gather(k_cache, v_cache, idx, n, offset, state=None, max_n=0, zero_tail=False):
+    """k_cache/v_cache (L,1,Hkv,M,D); idx int32 device tensor."""
+    lib = _lib.load()
+    L, _, Hkv, M, D = k_cache.shape
+    check(lib.sq_kv_gather(ptr(k_cache), ptr(v_cache), L, Hkv, M, D, ptr(idx), n, offset, ptr(state), max_n,
+                           1 if zero_tail else 0, stream_ptr()), "sq_kv_gather")
+
+
+class AttnPlan:
+    """TMA descriptors + split-KV workspace for one (qkv buffer, KV cache, output buffer) triple."""
+
+    def __init__(self, qkv: torch.Tensor, n_max: int, H: int, Hkv: int, D: int, k_cache, v_cache, out):
+        lib = _lib.load()
+        L, _, hk, M, d = k_cache.shape
+        assert hk == Hkv and d == D
+        nbytes = lib.sq_attn_workspace_bytes(n_max, H, D, M)
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=qkv.device)
+        self.handle = C.c_void_p()
+        self._keep = (qkv, k_cache, v_cache, out)
+        check(lib.sq_attn_plan_create(C.byref(self.handle), ptr(qkv), qkv.shape[-1], n_max, H, Hkv, D, ptr(k_cache),
+                                      ptr(v_cache), L, M, ptr(out), ptr(self.workspace), nbytes), "sq_attn_plan_create")
+        self.n_max, self.M = n_max, M
+
+    def error(self) -> int:
+        return _lib.load().sq_attn_plan_error(self.handle)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().sq_attn_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def tree_attn(plan: AttnPlan, layer, n, *, state=None, n0=0, kv_end=0, prefix_len=0, dense_mask=None, mask_ld=0,
+              tree_bits=None, tree_words=0, tree_size=0, impl=0):
+    lib = _lib.load()
+    check(lib.sq_tree_attn(plan.handle, layer, n, ptr(state), n0, kv_end, prefix_len, ptr(dense_mask), mask_ld,
+                           ptr(tree_bits), tree_words, tree_size, impl, stream_ptr()), "sq_tree_attn")
+
+
+def softmax_T(logits: torch.Tensor, T: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(logits, F16, "softmax_T")
+    lg = logits.reshape(-1, logits.shape[-1])
+    assert lg.stride(-1) == 1
+    if out is None:
+        out = torch.empty((lg.shape[0], lg.shape[1]), dtype=F16, device=logits.device)
+    lib = _lib.load()
+    check(lib.sq_softmax_T(ptr(lg), lg.stride(0), ptr(out), out.stride(0), lg.shape[0], lg.shape[1], T, stream_ptr()),
+          "sq_softmax_T")
+    return out.view(logits.shape) if out.numel() == logits.numel() else out
+
+
+def sample_level(logits, rand, n_parents, k_max, T, mode, *, parent_rows=None, child_first=None, n_branch=None,
+                 positions=None, tokens=None, state=None):
+    lib = _lib.load()
+    V = logits.shape[-1]
+    check(lib.sq_sample_level(ptr(logits), logits.stride(-2), ptr(rand), rand.stride(-2) if rand is not None else 0,
+                              ptr(parent_rows), ptr(child_first), ptr(n_branch), n_parents, k_max, V, T, mode,
+                              ptr(positions), ptr(tokens), ptr(state), stream_ptr()), "sq_sample_level")
+
+
+def residual(p, q, out=None):
+    _need(p, F16, "residual")
+    if out is None:
+        out = torch.empty_like(p)
+    check(_lib.load().sq_residual(ptr(p), ptr(q), ptr(out), p.shape[-1], stream_ptr()), "sq_residual")
+    return out
+
+
+def argmax_rows(logits, out=None):
+    n, V = logits.shape
+    if out is None:
+        out = torch.empty(n, dtype=torch.int64, device=logits.device)
+    check(_lib.load().sq_argmax_rows(ptr(logits), logits.stride(0), n, V, ptr(out), stream_ptr()), "sq_argmax_rows")
+    return out
+
+
+def accept_stochastic(target_logits, draft_logits, r, noise, succ_off, succ, depth, S, T, tokens, position_ids,
+                      accept_idx, state, max_target_seq):
+    V = target_logits.shape[-1]
+    check(_lib.load().sq_accept_stochastic(ptr(target_logits), target_logits.stride(0), ptr(draft_logits),
+                                           draft_logits.stride(0), ptr(r), ptr(noise), ptr(succ_off), ptr(succ),
+                                           ptr(depth), S, V, T, ptr(tokens), ptr(position_ids), ptr(accept_idx),
+                                           ptr(state), max_target_seq, stream_ptr()), "sq_accept_stochastic")
+
+
+def accept_greedy(target_token, succ_off, succ, depth, S, tokens, position_ids, accept_idx, state, max_target_seq):
+    check(_lib.load().sq_accept_greedy(ptr(target_token), ptr(succ_off), ptr(succ), ptr(depth), S, ptr(tokens),
+                                       ptr(position_ids), ptr(accept_idx), ptr(state), max_target_seq, stream_ptr()),
+          "sq_accept_greedy")
