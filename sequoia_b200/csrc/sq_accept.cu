@@ -1,71 +1,78 @@
 // Device-side verification walk (Tree/SpecTree.py:137-157,196-227,261-271; Tree/GreedyTree.py:132-146,186-240).
 // The reference walks the tree on the host with one D2H sync per tested child and ~6 tiny kernels each; here one
-// CTA keeps the target row p, the draft-logit row and the residual in registers, walks Successors (CSR), and then
-// applies the whole post-processing (token / position compaction, bonus token, state for the next iteration), so a
-// verify step needs no host round trip.  Latency-bound: ~2*V*2 bytes per visited parent.
+// 1024-thread CTA keeps the target distribution p and the temperature-scaled draft logits in registers, walks
+// Successors (CSR), and then applies the whole post-processing (token / position compaction, bonus token, state for
+// the next iteration), so a verify step needs no host round trip.  Latency / SFU-bound on one SM: ~2*V*2 bytes per
+// visited parent from HBM, V exp + V div per tested child.
+//
+// fp16 rounding chain of the reference reproduced step by step (see sq_sampling.cu for the conventions):
+//   p = fp16(softmax(fp16(t * 1/T)));  q = fp16(softmax(fp16(d * 1/T)));  accept iff p[tok] > fp16(r * q[tok])
+//   residual: d = relu(fp16(p - q)); s = fp16(sum d); p = fp16(d / s);  rejected token's draft logit -> fp16 min
+// The draft softmax is maintained incrementally: masking a token removes its exp from the running sum (the max only
+// has to be recomputed if the masked token was the max).
 #include "sq_common.cuh"
 
 namespace sq {
 
-constexpr int ANT = 512;
+constexpr int ANT = 1024;
 constexpr int ANW = ANT / 32;
-constexpr float FP16_MIN = -65504.f;
+constexpr int ACH = 4;   // 16-byte chunks per thread: V <= 32768
 
 __device__ __forceinline__ uint32_t a_ord16(__half h) {
   const uint32_t b = __half_as_ushort(h);
   return (b & 0x8000u) ? (~b & 0xFFFFu) : (b | 0x8000u);
 }
 
-template <int CH>
-__device__ __forceinline__ void a_load_row(const __half* __restrict__ row, int V, Pack8 (&x)[CH]) {
+// row striped over the block (chunk c = i*ANT + tid); out-of-range chunks read as -inf; scaled to fp16(x * inv_T)
+__device__ __forceinline__ void a_load_scaled(const __half* __restrict__ row, int V, float inv_T, Pack8 (&x)[ACH]) {
   const int nvec = V / 8;
 #pragma unroll
-  for (int i = 0; i < CH; ++i) {
+  for (int i = 0; i < ACH; ++i) {
     const int c = i * ANT + threadIdx.x;
-    if (c < nvec) x[i].u = reinterpret_cast<const uint4*>(row)[c];
+    if (c < nvec) {
+      x[i].u = reinterpret_cast<const uint4*>(row)[c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[i].h[j] = f2h(h2f(x[i].h[j]) * inv_T);
+    } else {
+      x[i].u = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
+    }
   }
 }
 
-template <int CH>
-__device__ __forceinline__ void a_stats(const Pack8 (&x)[CH], int V, float T, float* red, float& mx, float& sum) {
-  const int nvec = V / 8;
+__device__ __forceinline__ void a_stats(const Pack8 (&x)[ACH], float* red, float& mx, float& sum) {
   float m = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < CH; ++i)
-    if (i * ANT + threadIdx.x < nvec) {
+  for (int i = 0; i < ACH; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m = fmaxf(m, rnd16(h2f(x[i].h[j]) / T));
-    }
+    for (int j = 0; j < 8; ++j) m = fmaxf(m, h2f(x[i].h[j]));
   mx = block_max<ANW>(m, red);
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < CH; ++i)
-    if (i * ANT + threadIdx.x < nvec) {
+  for (int i = 0; i < ACH; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += expf(rnd16(h2f(x[i].h[j]) / T) - mx);
-    }
+    for (int j = 0; j < 8; ++j) s += __expf(h2f(x[i].h[j]) - mx);
   sum = block_sum<ANW>(s, red);
 }
 
-__device__ __forceinline__ __half a_softmax_val(__half x, float T, float mx, float sum) {
-  return f2h(expf(rnd16(h2f(x) / T) - mx) / sum);
-}
-
 // Post-processing shared by both walks.  Runs with the whole block; thread 0 does the (short, ordered) serial part.
-// sh_acc[0..n_new) = accepted absolute slots; returns nothing, publishes state[].
+// sh_acc[0..n_new) = accepted absolute slots; publishes state[].
+// bonus_first: SpecTree writes the bonus token at slot a BEFORE gathering tokens[accept_list] (SpecTree.py:222-224), so
+// an accepted node that happens to live at slot a is returned as the bonus token -- reproduced here; GreedyTree
+// gathers first (GreedyTree.py:205-207).
 __device__ void finish_verify(const int32_t* sh_acc, int n_new, int P, bool terminal, bool nan_flag, int64_t bonus,
-                              const int32_t* __restrict__ depth, int S, int64_t* __restrict__ tokens,
+                              bool bonus_first, const int32_t* __restrict__ depth, int S, int64_t* __restrict__ tokens,
                               int64_t* __restrict__ position_ids, int32_t* __restrict__ accept_idx,
                               int32_t* __restrict__ state, int max_target_seq) {
   const int a = P + n_new;
   const bool prepare = !terminal && (a + 1 <= max_target_seq);
   if (threadIdx.x == 0) {
+    if (!terminal && bonus_first) tokens[a] = bonus;        // SpecTree.py:222
     for (int j = 0; j < n_new; ++j) {                       // tokens[:a] = tokens[accept_list]  (SpecTree.py:224)
       const int src = sh_acc[j];
       accept_idx[j] = src;
       tokens[P + j] = tokens[src];
     }
-    if (!terminal) tokens[a] = bonus;                       // SpecTree.py:222 / GreedyTree.py:207
+    if (!terminal && !bonus_first) tokens[a] = bonus;       // GreedyTree.py:207
     if (prepare) {                                          // prepare_for_next_iter (SpecTree.py:261-271)
       for (int j = 0; j < n_new; ++j) position_ids[P + j] = position_ids[sh_acc[j]];
       position_ids[a] = a;
@@ -79,96 +86,99 @@ __device__ void finish_verify(const int32_t* sh_acc, int n_new, int P, bool term
     state[ST_SKIPPED] = (!terminal && !prepare) ? 1 : 0;
     if (prepare) state[ST_P] = a + 1;
   }
+  __syncthreads();   // the gather above reads old tree positions that the re-lay below overwrites
   if (prepare) {
     for (int k = 1 + threadIdx.x; k < S; k += blockDim.x) position_ids[a + k] = (int64_t)depth[k] + a;
   }
 }
 
-template <int CH>
 __global__ void __launch_bounds__(ANT) accept_stochastic_kernel(
     const __half* __restrict__ target_logits, int64_t ld_t, const __half* __restrict__ draft_logits, int64_t ld_d,
     const __half* __restrict__ r, const __half* __restrict__ noise, const int32_t* __restrict__ succ_off,
-    const int32_t* __restrict__ succ, const int32_t* __restrict__ depth, int S, int V, float T,
+    const int32_t* __restrict__ succ, const int32_t* __restrict__ depth, int S, int V, float inv_T,
     int64_t* __restrict__ tokens, int64_t* __restrict__ position_ids, int32_t* __restrict__ accept_idx,
     int32_t* __restrict__ state, int max_target_seq) {
   __shared__ float red[ANW];
   __shared__ uint32_t redu[ANW];
   __shared__ int32_t sh_acc[1024];
+  __shared__ float sh_etok;
   __shared__ int sh_flag;
   const int P = state[ST_P];
   const int nvec = V / 8;
-  Pack8 p[CH], dl[CH];
+  Pack8 p[ACH], xd[ACH];
   int cur = 0, n_new = 0;
   bool terminal = false;
   while (true) {
     // p = softmax(target_logits[cur] / T)   (SpecTree.py:198, computed lazily for visited parents only)
-    a_load_row<CH>(target_logits + cur * ld_t, V, p);
+    a_load_scaled(target_logits + cur * ld_t, V, inv_T, p);
     {
       float mx, sum;
-      a_stats<CH>(p, V, T, red, mx, sum);
+      a_stats(p, red, mx, sum);
 #pragma unroll
-      for (int i = 0; i < CH; ++i)
-        if (i * ANT + threadIdx.x < nvec) {
+      for (int i = 0; i < ACH; ++i)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) p[i].h[e] = a_softmax_val(p[i].h[e], T, mx, sum);
-        }
+        for (int e = 0; e < 8; ++e) p[i].h[e] = f2h(__fdividef(__expf(h2f(p[i].h[e]) - mx), sum));
     }
     const int c0 = succ_off[cur], c1 = succ_off[cur + 1];
     if (c0 == c1) break;                                     // leaf: residual = p   (SpecTree.py:143-144)
-    a_load_row<CH>(draft_logits + cur * ld_d, V, dl);
+    a_load_scaled(draft_logits + cur * ld_d, V, inv_T, xd);
+    float mxd, sumd;
+    a_stats(xd, red, mxd, sumd);                             // q = softmax(draft_logits / T)  (:149)
     int accepted = -1;
     for (int ci = c0; ci < c1; ++ci) {
       const int child = succ[ci];
       const int slot = P - 1 + child;
       const int tok = (int)tokens[slot];
-      float mx, sum;
-      a_stats<CH>(dl, V, T, red, mx, sum);                   // q = softmax(draft_logits / T)  (:149)
       const int tc = tok >> 3, te = tok & 7;
-      if (threadIdx.x == (tc % ANT)) {
+      const bool owner = (threadIdx.x == (tc % ANT));
+      if (owner) {
         const int ti = tc / ANT;
         __half ptok = f2h(0.f), dtok = f2h(0.f);
 #pragma unroll
-        for (int i = 0; i < CH; ++i)
+        for (int i = 0; i < ACH; ++i)
 #pragma unroll
           for (int e = 0; e < 8; ++e)
-            if (i == ti && e == te) { ptok = p[i].h[e]; dtok = dl[i].h[e]; }
-        const float qtok = h2f(a_softmax_val(dtok, T, mx, sum));
+            if (i == ti && e == te) { ptok = p[i].h[e]; dtok = xd[i].h[e]; }
+        const float etok = __expf(h2f(dtok) - mxd);
+        const float qtok = h2f(f2h(__fdividef(etok, sumd)));
         const float thr = rnd16(h2f(r[slot]) * qtok);        // r * q[token] in fp16
-        sh_flag = (h2f(ptok) > thr) ? 1 : 0;                 // strict >   (:152)
+        const int acc = (h2f(ptok) > thr) ? 1 : 0;           // strict >   (:152)
+        sh_flag = acc | ((h2f(dtok) >= mxd) ? 2 : 0);        // bit 1: the rejected token holds the running max
+        sh_etok = etok;
       }
       __syncthreads();
-      const int acc = sh_flag;
+      const int flag = sh_flag;
+      const float etok = sh_etok;
       __syncthreads();
-      if (acc) { accepted = child; break; }
-      // p = get_residual(p, q) ; draft_logits[token] = fp16 min   (:155-156)
+      if (flag & 1) { accepted = child; break; }
+      // p = get_residual(p, q)   (:155, utils.py:5-8)
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < CH; ++i)
-        if (i * ANT + threadIdx.x < nvec) {
+      for (int i = 0; i < ACH; ++i)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float q = h2f(a_softmax_val(dl[i].h[e], T, mx, sum));
-            float d = rnd16(h2f(p[i].h[e]) - q);
-            d = (d < 0.f) ? 0.f : d;
-            p[i].h[e] = f2h(d);
-            s += d;
-          }
+        for (int e = 0; e < 8; ++e) {
+          const float q = h2f(f2h(__fdividef(__expf(h2f(xd[i].h[e]) - mxd), sumd)));
+          float d = rnd16(h2f(p[i].h[e]) - q);
+          d = (d < 0.f) ? 0.f : d;                           // relu_; NaN propagates like torch
+          p[i].h[e] = f2h(d);
+          s += d;
         }
       const float tot = rnd16(block_sum<ANW>(s, red));
 #pragma unroll
-      for (int i = 0; i < CH; ++i)
-        if (i * ANT + threadIdx.x < nvec) {
+      for (int i = 0; i < ACH; ++i)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) p[i].h[e] = f2h(h2f(p[i].h[e]) / tot);
-        }
-      if (threadIdx.x == (tc % ANT)) {
+        for (int e = 0; e < 8; ++e) p[i].h[e] = f2h(h2f(p[i].h[e]) / tot);
+      // draft_logits[token] = fp16 min   (:156)  ->  scaled value -inf, exp 0
+      if (owner) {
         const int ti = tc / ANT;
 #pragma unroll
-        for (int i = 0; i < CH; ++i)
+        for (int i = 0; i < ACH; ++i)
 #pragma unroll
           for (int e = 0; e < 8; ++e)
-            if (i == ti && e == te) dl[i].h[e] = f2h(FP16_MIN);
+            if (i == ti && e == te) xd[i].h[e] = __ushort_as_half((unsigned short)0xFC00u);
       }
+      if (flag & 2) a_stats(xd, red, mxd, sumd);             // rare: the max left the support
+      else sumd -= etok;
     }
     if (accepted < 0) break;                                 // residual = p   (:157)
     const int slot = P - 1 + accepted;
@@ -184,7 +194,7 @@ __global__ void __launch_bounds__(ANT) accept_stochastic_kernel(
   if (!terminal) {
     int has_nan = 0;
 #pragma unroll
-    for (int i = 0; i < CH; ++i)
+    for (int i = 0; i < ACH; ++i)
       if (i * ANT + threadIdx.x < nvec) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) has_nan |= __hisnan(p[i].h[e]) ? 1 : 0;
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__(ANT) accept_stochastic_kernel(
       // residual.multinomial(1): argmax(residual / Exp(1) noise)   (:222, torch's n=1 form)
       uint32_t best = 0u;
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
+      for (int i = 0; i < ACH; ++i) {
         const int c = i * ANT + threadIdx.x;
         if (c < nvec) {
           Pack8 nz;
@@ -211,11 +221,11 @@ __global__ void __launch_bounds__(ANT) accept_stochastic_kernel(
       best = __reduce_max_sync(0xffffffffu, best);
       if ((threadIdx.x & 31) == 0) redu[threadIdx.x >> 5] = best;
       __syncthreads();
-      best = __reduce_max_sync(0xffffffffu, (threadIdx.x & 31) < ANW ? redu[threadIdx.x & 31] : 0u);
+      best = __reduce_max_sync(0xffffffffu, redu[threadIdx.x & 31]);
       bonus = (int64_t)(0xFFFFu - (best & 0xFFFFu));
     }
   }
-  finish_verify(sh_acc, n_new, P, terminal, nan_flag, bonus, depth, S, tokens, position_ids, accept_idx, state,
+  finish_verify(sh_acc, n_new, P, terminal, nan_flag, bonus, true, depth, S, tokens, position_ids, accept_idx, state,
                 max_target_seq);
 }
 
@@ -249,8 +259,8 @@ __global__ void accept_greedy_kernel(const int64_t* __restrict__ target_token, c
     sh_bonus = term ? -1 : target_token[cur];                // GreedyTree.py:207
   }
   __syncthreads();
-  finish_verify(sh_acc, sh_n, P, sh_term != 0, false, (int64_t)sh_bonus, depth, S, tokens, position_ids, accept_idx,
-                state, max_target_seq);
+  finish_verify(sh_acc, sh_n, P, sh_term != 0, false, (int64_t)sh_bonus, false, depth, S, tokens, position_ids,
+                accept_idx, state, max_target_seq);
 }
 
 }  // namespace sq
@@ -262,17 +272,11 @@ extern "C" int sq_accept_stochastic(const sq_half* target_logits, int64_t ld_t, 
                                     const int32_t* succ, const int32_t* depth, int S, int V, float T, int64_t* tokens,
                                     int64_t* position_ids, int32_t* accept_idx, int32_t* state, int max_target_seq,
                                     void* stream) {
-  SQ_CHECK_ARG(V % 8 == 0 && V > 0 && V <= 32768, "sq_accept_stochastic: V=%d unsupported", V);
+  SQ_CHECK_ARG(V % 8 == 0 && V > 0 && V <= ANT * ACH * 8, "sq_accept_stochastic: V=%d unsupported", V);
   SQ_CHECK_ARG(S >= 1 && S <= 1024, "sq_accept_stochastic: S=%d unsupported", S);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (V <= 16384)
-    accept_stochastic_kernel<4><<<1, ANT, 0, st>>>((const __half*)target_logits, ld_t, (const __half*)draft_logits, ld_d,
-                                                  (const __half*)r, (const __half*)noise, succ_off, succ, depth, S, V, T,
-                                                  tokens, position_ids, accept_idx, state, max_target_seq);
-  else
-    accept_stochastic_kernel<8><<<1, ANT, 0, st>>>((const __half*)target_logits, ld_t, (const __half*)draft_logits, ld_d,
-                                                  (const __half*)r, (const __half*)noise, succ_off, succ, depth, S, V, T,
-                                                  tokens, position_ids, accept_idx, state, max_target_seq);
+  accept_stochastic_kernel<<<1, ANT, 0, (cudaStream_t)stream>>>(
+      (const __half*)target_logits, ld_t, (const __half*)draft_logits, ld_d, (const __half*)r, (const __half*)noise,
+      succ_off, succ, depth, S, V, 1.0f / T, tokens, position_ids, accept_idx, state, max_target_seq);
   SQ_CHECK_LAUNCH("sq_accept_stochastic");
   return SQ_OK;
 }

@@ -204,6 +204,9 @@ class GraphInferenceEngineTG:
                                         device=device, offloading=offloading, tp_group=tp_group)
 
     def clear_kv(self):
+        drv = getattr(self, "_tp_driver", None)
+        if drv is not None:
+            drv.send_ctrl(3)                             # OP_CLEAR: follower ranks clear their shards too
         self.engine.clear_kv()
 
     def initialize_kv(self, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int):

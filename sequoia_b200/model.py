@@ -159,6 +159,33 @@ class TPInfo:
             dist.all_reduce(t, group=self.group)
 
 
+def load_sharded_weights(cfg: LlamaConfigLite, src, rank: int, tp: int) -> dict:
+    """Megatron-style shard `rank` of `tp`: q/k/v and gate/up split by output rows (heads / FFN columns) and fused,
+    o_proj / down_proj split by input columns (their partial products are summed by the allreduce)."""
+    h, D, V = cfg.hidden_size, cfg.head_dim, cfg.vocab_size
+    Hf, Hkvf, If = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.intermediate_size
+    assert Hf % tp == 0 and Hkvf % tp == 0 and If % tp == 0, "heads / FFN width must divide the TP degree"
+    H, Hkv, I, r = Hf // tp, Hkvf // tp, If // tp, rank
+    out = {"embed": src.get("model.embed_tokens.weight", (V, h)), "layers": []}
+    for l in range(cfg.num_hidden_layers):
+        p = f"model.layers.{l}."
+        wq = src.get(p + "self_attn.q_proj.weight", (Hf * D, h))[r * H * D:(r + 1) * H * D]
+        wk = src.get(p + "self_attn.k_proj.weight", (Hkvf * D, h))[r * Hkv * D:(r + 1) * Hkv * D]
+        wv = src.get(p + "self_attn.v_proj.weight", (Hkvf * D, h))[r * Hkv * D:(r + 1) * Hkv * D]
+        wo = src.get(p + "self_attn.o_proj.weight", (h, Hf * D))[:, r * H * D:(r + 1) * H * D]
+        wg = src.get(p + "mlp.gate_proj.weight", (If, h))[r * I:(r + 1) * I]
+        wu = src.get(p + "mlp.up_proj.weight", (If, h))[r * I:(r + 1) * I]
+        wd = src.get(p + "mlp.down_proj.weight", (h, If))[:, r * I:(r + 1) * I]
+        out["layers"].append(dict(
+            wqkv=torch.cat([wq, wk, wv], dim=0).contiguous(), wo=wo.contiguous(),
+            wgu=torch.cat([wg, wu], dim=0).contiguous(), wd=wd.contiguous(),
+            ln1=src.get(p + "input_layernorm.weight", (h,)), ln2=src.get(p + "post_attention_layernorm.weight", (h,))))
+        del wq, wk, wv, wo, wg, wu, wd
+    out["norm"] = src.get("model.norm.weight", (h,))
+    out["lm_head"] = src.get("lm_head.weight", (V, h))
+    return out
+
+
 class LlamaRunner:
     """Weights + preallocated activations + attention plan of one engine."""
 
@@ -175,25 +202,8 @@ class LlamaRunner:
         self.I = cfg.intermediate_size // tp
         h, D, V = cfg.hidden_size, self.D, cfg.vocab_size
         self.h, self.V, self.L = h, V, cfg.num_hidden_layers
-        Hf, Hkvf, If = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.intermediate_size
-        self.embed = src.get("model.embed_tokens.weight", (V, h))
-        self.layers = []
-        for l in range(self.L):
-            p = f"model.layers.{l}."
-            wq = src.get(p + "self_attn.q_proj.weight", (Hf * D, h))[r * self.H * D:(r + 1) * self.H * D]
-            wk = src.get(p + "self_attn.k_proj.weight", (Hkvf * D, h))[r * self.Hkv * D:(r + 1) * self.Hkv * D]
-            wv = src.get(p + "self_attn.v_proj.weight", (Hkvf * D, h))[r * self.Hkv * D:(r + 1) * self.Hkv * D]
-            wo = src.get(p + "self_attn.o_proj.weight", (h, Hf * D))[:, r * self.H * D:(r + 1) * self.H * D]
-            wg = src.get(p + "mlp.gate_proj.weight", (If, h))[r * self.I:(r + 1) * self.I]
-            wu = src.get(p + "mlp.up_proj.weight", (If, h))[r * self.I:(r + 1) * self.I]
-            wd = src.get(p + "mlp.down_proj.weight", (h, If))[:, r * self.I:(r + 1) * self.I]
-            self.layers.append(dict(
-                wqkv=torch.cat([wq, wk, wv], dim=0).contiguous(), wo=wo.contiguous(),
-                wgu=torch.cat([wg, wu], dim=0).contiguous(), wd=wd.contiguous(),
-                ln1=src.get(p + "input_layernorm.weight", (h,)), ln2=src.get(p + "post_attention_layernorm.weight", (h,))))
-            del wq, wk, wv, wo, wg, wu, wd
-        self.norm = src.get("model.norm.weight", (h,))
-        self.lm_head = src.get("lm_head.weight", (V, h))
+        wts = load_sharded_weights(cfg, src, r, tp)
+        self.embed, self.layers, self.norm, self.lm_head = wts["embed"], wts["layers"], wts["norm"], wts["lm_head"]
         self.cos, self.sin = rope_cache(cfg, max_length, self.device)
         self.eps = float(cfg.rms_norm_eps)
         n = self.n_max
@@ -219,7 +229,7 @@ class LlamaRunner:
     def forward(self, n: int, tokens: torch.Tensor, position_ids: torch.Tensor, storage_ids: torch.Tensor, *,
                 state=None, n0: int = 0, kv_end: int = 0, prefix_len: int = 0, dense_mask=None, mask_ld: int = 0,
                 tree_bits=None, tree_words: int = 0, tree_size: int = 0, logits_out: Optional[torch.Tensor] = None,
-                logits_from: int = 0) -> torch.Tensor:
+                logits_from: int = 0, skip_lm_head: bool = False) -> Optional[torch.Tensor]:
         """Forward `n` rows.  Row r is token tokens[base+r] at position position_ids[base+r], written to cache slot
         storage_ids[base+r], base = (state ? P-1 : 0) + n0.  Attends slots [0, (state ? P-1 : 0) + kv_end).
         Logits of rows [logits_from, n) are written to `logits_out` (default: the internal buffer) and returned."""
@@ -244,6 +254,8 @@ class LlamaRunner:
             self.tp.all_reduce(self.proj[:n])
             nxt = self.layers[l + 1]["ln1"] if l + 1 < self.L else self.norm
             ops.add_rmsnorm(self.hidden, self.proj, nxt, self.normed, n, self.eps)
+        if skip_lm_head:                               # TP follower ranks: only rank 0 consumes logits
+            return None
         m = n - logits_from
         out = logits_out if logits_out is not None else self.logits[:m]
         torch.mm(self.normed[logits_from:n], self.lm_head.t(), out=out)

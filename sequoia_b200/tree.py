@@ -149,8 +149,15 @@ class _Runtime:
         self.draft.engine.runner.forward(tb, self.tokens, self.position_ids, self.storage_ids, state=self.state, n0=n0,
                                          kv_end=n0 + tb, logits_out=self.draft_logits[n0:n0 + tb], **self._mask_kw())
 
+    @property
+    def tp(self):
+        """TPDriver when the target is tensor-parallel over several ranks (sequoia_b200.tp), else None."""
+        return getattr(self.target, "_tp_driver", None)
+
     def op_target_steady(self):
         S = self.st.S
+        if self.tp is not None:
+            self.tp.bcast_inputs(self)
         self.target.engine.runner.forward(S, self.tokens, self.position_ids, self.storage_ids, state=self.state, n0=0,
                                           kv_end=S, logits_out=self.target_logits, **self._mask_kw())
 
@@ -159,6 +166,8 @@ class _Runtime:
         S = self.st.S
         end = P + S - 1
         n = end - start
+        if self.tp is not None:
+            self.tp.bcast_inputs(self)
         self.target.engine.runner.forward(n, self.tokens, self.position_ids, self.storage_ids, state=None, n0=start,
                                           kv_end=end, prefix_len=P, logits_out=self.target_logits, logits_from=n - S,
                                           **self._mask_kw())
@@ -180,6 +189,8 @@ class _Runtime:
 
     def op_kv_gather(self):
         md = max(self.st.max_depth, 1)
+        if self.tp is not None:
+            self.tp.bcast_accept(self)
         self.draft.engine.kv_cache.gather_from_state(self.accept_idx, self.state, md)   # SpecTree.py:226-227
         self.target.engine.kv_cache.gather_from_state(self.accept_idx, self.state, md)
 
@@ -428,6 +439,8 @@ class _TreeBase(Tree):
         if benchmark:
             torch.cuda.synchronize()
             t1 = time.time()
+            if rt.tp is not None:
+                rt.tp.send_ctrl(1 if steady else 2, self.target_kv_len, P)
             if steady:
                 rt.op_target_steady()
             else:
@@ -443,10 +456,17 @@ class _TreeBase(Tree):
             rt.op_bonus_forward()
             rt.op_publish()
         elif steady:
+            if rt.tp is not None:
+                rt.tp.send_ctrl(1)                       # OP_STEADY
             rt.run("steady", rt.seq_steady)
         else:
-            rt.op_target_first(self.target_kv_len, P)
-            rt.run("post", rt.seq_post)
+            if rt.tp is not None:
+                rt.tp.send_ctrl(2, self.target_kv_len, P)   # OP_FIRST; its post-processing stays eager so that the
+                rt.op_target_first(self.target_kv_len, P)    # follower ranks see each collective exactly once
+                rt.seq_post()
+            else:
+                rt.op_target_first(self.target_kv_len, P)
+                rt.run("post", rt.seq_post)
         torch.cuda.current_stream().synchronize()       # the one host sync of a verify step
         rt.iter += 1
         hs = rt.host_state

@@ -66,11 +66,11 @@ DECODE_CASES = {
     # name: (growmap, mode, draft cfg/seed, target cfg/seed, M, prompt seed, prefix, iters, rng seed)
     "greedy_2chain": ("L40_growmaps/2-chain.pt", "greedy", "draft", "target", 256, 11, 96, 6, 17),
     "greedy_4x4": ("L40_growmaps/4x4-tree.pt", "greedy", "draft", "target", 256, 12, 64, 5, 17),
-    "spec_8x8": ("L40_growmaps/8x8-tree.pt", "spec", "draft", "target", 256, 13, 100, 5, 17),
+    "spec_8x8": ("L40_growmaps/8x8-tree.pt", "spec", "draft", "target", 256, 25, 100, 5, 17),
     "spec_a100_128": ("A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt", "spec", "draft", "target_gqa",
-                      384, 14, 128, 4, 17),
+                      384, 22, 128, 4, 17),
     # draft == target weights: forces deep acceptance paths / multi-row KV gathers
-    "spec_same_8x8": ("L40_growmaps/8x8-tree.pt", "spec", "draft", "draft", 256, 15, 80, 5, 17),
+    "spec_same_8x8": ("L40_growmaps/8x8-tree.pt", "spec", "draft", "draft", 256, 26, 80, 5, 17),
     "greedy_same_16chain": ("L40_growmaps/16-chain.pt", "greedy", "draft", "draft", 256, 16, 70, 4, 17),
 }
 
