@@ -10,7 +10,10 @@
 //   residual: d = relu(fp16(p - q)); s = fp16(sum d); p = fp16(d / s);  rejected token's draft logit -> fp16 min
 // The draft softmax is maintained incrementally: masking a token removes its exp from the running sum (the max only
 // has to be recomputed if the masked token was the max).
+#include <cstdlib>
+
 #include "sq_common.cuh"
+#include "sq_accept_common.cuh"
 
 namespace sq {
 
@@ -52,44 +55,6 @@ __device__ __forceinline__ void a_stats(const Pack8 (&x)[ACH], float* red, float
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += __expf(h2f(x[i].h[j]) - mx);
   sum = block_sum<ANW>(s, red);
-}
-
-// Post-processing shared by both walks.  Runs with the whole block; thread 0 does the (short, ordered) serial part.
-// sh_acc[0..n_new) = accepted absolute slots; publishes state[].
-// bonus_first: SpecTree writes the bonus token at slot a BEFORE gathering tokens[accept_list] (SpecTree.py:222-224), so
-// an accepted node that happens to live at slot a is returned as the bonus token -- reproduced here; GreedyTree
-// gathers first (GreedyTree.py:205-207).
-__device__ void finish_verify(const int32_t* sh_acc, int n_new, int P, bool terminal, bool nan_flag, int64_t bonus,
-                              bool bonus_first, const int32_t* __restrict__ depth, int S, int64_t* __restrict__ tokens,
-                              int64_t* __restrict__ position_ids, int32_t* __restrict__ accept_idx,
-                              int32_t* __restrict__ state, int max_target_seq) {
-  const int a = P + n_new;
-  const bool prepare = !terminal && (a + 1 <= max_target_seq);
-  if (threadIdx.x == 0) {
-    if (!terminal && bonus_first) tokens[a] = bonus;        // SpecTree.py:222
-    for (int j = 0; j < n_new; ++j) {                       // tokens[:a] = tokens[accept_list]  (SpecTree.py:224)
-      const int src = sh_acc[j];
-      accept_idx[j] = src;
-      tokens[P + j] = tokens[src];
-    }
-    if (!terminal && !bonus_first) tokens[a] = bonus;       // GreedyTree.py:207
-    if (prepare) {                                          // prepare_for_next_iter (SpecTree.py:261-271)
-      for (int j = 0; j < n_new; ++j) position_ids[P + j] = position_ids[sh_acc[j]];
-      position_ids[a] = a;
-    }
-    state[ST_ACCEPT_LEN] = a;
-    state[ST_TERMINAL] = terminal ? 1 : 0;
-    state[ST_N_NEW] = n_new;
-    state[ST_P_OLD] = P;
-    state[ST_BONUS] = terminal ? -1 : (int32_t)bonus;
-    state[ST_NAN] = nan_flag ? 1 : 0;
-    state[ST_SKIPPED] = (!terminal && !prepare) ? 1 : 0;
-    if (prepare) state[ST_P] = a + 1;
-  }
-  __syncthreads();   // the gather above reads old tree positions that the re-lay below overwrites
-  if (prepare) {
-    for (int k = 1 + threadIdx.x; k < S; k += blockDim.x) position_ids[a + k] = (int64_t)depth[k] + a;
-  }
 }
 
 __global__ void __launch_bounds__(ANT) accept_stochastic_kernel(
@@ -274,6 +239,10 @@ extern "C" int sq_accept_stochastic(const sq_half* target_logits, int64_t ld_t, 
                                     void* stream) {
   SQ_CHECK_ARG(V % 8 == 0 && V > 0 && V <= ANT * ACH * 8, "sq_accept_stochastic: V=%d unsupported", V);
   SQ_CHECK_ARG(S >= 1 && S <= 1024, "sq_accept_stochastic: S=%d unsupported", S);
+  static const int impl = [] { const char* e = getenv("SQ_ACCEPT_IMPL"); return e ? atoi(e) : 1; }();
+  if (impl == 1)   // product path: 8-CTA cluster kernel (sq_accept_cluster.cu); impl 0 = single-CTA cross-check
+    return sq::launch_accept_cluster(target_logits, ld_t, draft_logits, ld_d, r, noise, succ_off, succ, depth, S, V, T,
+                                     tokens, position_ids, accept_idx, state, max_target_seq, stream);
   accept_stochastic_kernel<<<1, ANT, 0, (cudaStream_t)stream>>>(
       (const __half*)target_logits, ld_t, (const __half*)draft_logits, ld_d, (const __half*)r, (const __half*)noise,
       succ_off, succ, depth, S, V, 1.0f / T, tokens, position_ids, accept_idx, state, max_target_seq);

@@ -14,6 +14,7 @@
 // Roofline: HBM-bound for configs 2/3 (bytes = 2*D*2*(Hkv*kv + H*q) per layer), tensor-pipe-bound for config 4.
 //
 // impl 1 is a plain SIMT kernel used by the tests as an on-device cross-check of the tensor-core path.
+#include <cooperative_groups.h>
 #include <cuda.h>
 
 #include <cstdio>
@@ -32,6 +33,7 @@ struct sq_attn_plan {
   int n_pad, splits_max;
   int debug_flags;
   int* err_flag;  // device word set by a watchdog timeout
+  int* counters;  // [H][n_pad/128] split arrival counters
   CUtensorMap tm_q, tm_k, tm_v;
 };
 
@@ -60,6 +62,7 @@ struct AttnArgs {
   float scale;
   int debug_flags;
   int* err_flag;
+  int* counters;           // [H][q_tiles] arrival counters of the split-KV CTAs (self-resetting)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -296,22 +299,32 @@ struct TcSmem {
   static constexpr int OFF_V = 2 * TILE_BYTES;
   static constexpr int OFF_MASK = 3 * TILE_BYTES;       // 128 x 132 halfs (dense) or 128 x tree_words u32 (bits)
   static constexpr int MASK_BYTES = 128 * 132 * 2;
-  static constexpr int OFF_BAR = OFF_MASK + MASK_BYTES; // 3 mbarriers + tmem ptr
+  static constexpr int OFF_ML = OFF_MASK + MASK_BYTES;  // per-row (max, sum) of this split: 128 x float2
+  static constexpr int OFF_BAR = OFF_ML + 1024;         // 3 mbarriers + tmem ptr
   static constexpr int TOTAL = OFF_BAR + 64;
+  // after the second MMA the Q/K/V tiles are dead: the fp32 partial O (128 x (D+4)) is published there for the
+  // cluster-wide split-KV reduction through distributed shared memory
+  static constexpr int O_STRIDE = D + 4;                // floats; +4 keeps the row-per-thread float4 stores conflict-free
+  static_assert(128 * O_STRIDE * 4 <= 3 * TILE_BYTES, "partial O must fit in the dead Q/K/V tiles");
 };
 
-// impl 0: grid (H, q_tiles, kv_splits), 128 threads.
-template <int D>
+// impl 0.  grid (H, q_tiles, Z) launched as thread-block clusters (1,1,Z), Z = ceil(M/128) <= 8: the CTAs of one
+// cluster are the KV splits of one (head, q tile).  128 threads, thread == query row == TMEM lane.
+// The loops over 32-column TMEM chunks are deliberately NOT unrolled: every instruction of this kernel runs once per
+// CTA, so code size (instruction-fetch latency) matters more than ILP.
+template <int D, bool DENSE>
 __global__ void __launch_bounds__(128, 1)
     tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, AttnArgs a) {
   using SM = TcSmem<D>;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem base is only guaranteed 16 B aligned: re-align to 1024 B for SWIZZLE_128B
+  // dynamic smem base is only guaranteed 16 B aligned: re-align to 1024 B for SWIZZLE_128B (same offset in every CTA)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int h = blockIdx.x, qt = blockIdx.y, split = blockIdx.z;
+  const int h = blockIdx.x, qt = blockIdx.y, split = blockIdx.z, Z = gridDim.z;
   const int hkv = h / (a.H / a.Hkv);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P = a.state ? a.state[ST_P] : a.prefix_len_host;
   const int base = a.state ? (P - 1) : 0;
   const int kv_len = base + a.kv_end;
@@ -319,199 +332,225 @@ __global__ void __launch_bounds__(128, 1)
   const int q0 = qt * TILE_Q;
   const int row = q0 + tid;                      // this thread's query row (TMEM lane tid)
   const int slot = base + a.n0 + row;
-  float* ws_ml = a.ws_ml + (((int64_t)split * a.H + h) * a.n_pad + row) * 2;
-  float* ws_o = a.ws_o + (((int64_t)split * a.H + h) * a.n_pad + row) * D;
+  const int nsplit = (kv_len + TILE_KV - 1) / TILE_KV;
 
-  if (kv0 >= kv_len) return;                     // inactive split (combine only reads ceil(kv_len/128) splits)
-  // whole tile masked for every row of this q tile?  (structured mode only)
-  if (!a.dense_mask) {
+  bool active = kv0 < kv_len;
+  if (active && !DENSE) {                        // whole tile masked for every row of this q tile?
     const int last_slot = base + a.n0 + min(q0 + TILE_Q, a.n) - 1;
     const int max_vis = (last_slot >= P) ? (kv_len - 1) : min(last_slot, P - 1);
-    if (kv0 > max_vis) {
-      if (row < a.n) { ws_ml[0] = -INFINITY; ws_ml[1] = 0.f; }
-      return;
+    active = kv0 <= max_vis;
+  }
+  float* sO = reinterpret_cast<float*>(smem);
+  float2* sML = reinterpret_cast<float2*>(smem + SM::OFF_ML);
+  float mx = -INFINITY, lsum = 0.f;
+
+  if (active) {
+    const uint32_t sQ = ptx::smem_u32(smem + SM::OFF_Q), sK = ptx::smem_u32(smem + SM::OFF_K),
+                   sV = ptx::smem_u32(smem + SM::OFF_V);
+    const uint32_t bar_qk = ptx::smem_u32(smem + SM::OFF_BAR), bar_v = bar_qk + 8, bar_mma = bar_qk + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + 32);
+    if (tid == 0) {
+      ptx::mbar_init(bar_qk, 1);
+      ptx::mbar_init(bar_v, 1);
+      ptx::mbar_init(bar_mma, 1);
+      ptx::fence_barrier_init();
     }
-  }
-
-  const uint32_t sQ = ptx::smem_u32(smem + SM::OFF_Q), sK = ptx::smem_u32(smem + SM::OFF_K),
-                 sV = ptx::smem_u32(smem + SM::OFF_V);
-  const uint32_t bar_qk = ptx::smem_u32(smem + SM::OFF_BAR), bar_v = bar_qk + 8, bar_mma = bar_qk + 16;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + 32);
-
-  if (tid == 0) {
-    ptx::mbar_init(bar_qk, 1);
-    ptx::mbar_init(bar_v, 1);
-    ptx::mbar_init(bar_mma, 1);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 0) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 256);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_ptr_smem;
-  const uint32_t tm_S = tmem;                    // 128 fp32 columns
-  const uint32_t tm_P = tmem;                    // 64 columns (fp16 pairs), aliases S
-  const uint32_t tm_O = tmem + 128;              // D fp32 columns
-
-  if (tid == 0) {
-    ptx::mbar_expect_tx(bar_qk, 2 * SM::TILE_BYTES);
-    ptx::mbar_expect_tx(bar_v, SM::TILE_BYTES);
-#pragma unroll
-    for (int hh = 0; hh < SM::HALVES; ++hh) {
-      ptx::tma_load_2d(sQ + hh * 16384, &tm_q, bar_qk, h * D + hh * 64, q0);
-      ptx::tma_load_3d(sK + hh * 16384, &tm_k, bar_qk, hh * 64, kv0, a.layer * a.Hkv + hkv);
+    if (warp == 0) {
+      ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 256);
+      ptx::tmem_relinquish();
     }
-#pragma unroll
-    for (int hh = 0; hh < SM::HALVES; ++hh)
-      ptx::tma_load_3d(sV + hh * 16384, &tm_v, bar_v, hh * 64, kv0, a.layer * a.Hkv + hkv);
-  }
-
-  // stage the mask of this (q tile, kv tile) in shared memory while the TMA loads fly
-  const RowMask rm = row_mask(slot, P);
-  uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + SM::OFF_MASK);
-  __half* smask = reinterpret_cast<__half*>(smem + SM::OFF_MASK);
-  if (a.dense_mask) {
-    for (int i = tid; i < TILE_Q * TILE_KV; i += 128) {
-      const int rr = i / TILE_KV, cc = i % TILE_KV;
-      __half v = __float2half(0.f);
-      if (q0 + rr < a.n && kv0 + cc < kv_len) v = a.dense_mask[(int64_t)(q0 + rr) * a.mask_ld + kv0 + cc];
-      smask[rr * 132 + cc] = v;
-    }
-  } else if (a.tree_bits) {
-    for (int i = tid; i < TILE_Q * a.tree_words; i += 128) {
-      const int rr = i / a.tree_words, w = i % a.tree_words;
-      const int node = base + a.n0 + q0 + rr - (P - 1);
-      sbits[i] = (node >= 1 && node < a.tree_size) ? a.tree_bits[(int64_t)node * a.tree_words + w] : 0u;
-    }
-  }
-  __syncthreads();
-
-  // ---- S = Q K^T --------------------------------------------------------------------------------------------------
-  if (tid == 0) {
-    ptx::mbar_wait_one(bar_qk, 0, a.err_flag, 1);
+    ptx::tc_fence_before();
+    __syncthreads();
     ptx::tc_fence_after();
-    constexpr uint32_t idesc = umma_idesc(TILE_KV, false);
+    const uint32_t tmem = *tmem_ptr_smem;
+    const uint32_t tm_S = tmem;                  // 128 fp32 columns
+    const uint32_t tm_P = tmem;                  // 64 columns (fp16 pairs), aliases S
+    const uint32_t tm_O = tmem + 128;            // D fp32 columns
+    if (tid == 0) {
+      ptx::mbar_expect_tx(bar_qk, 2 * SM::TILE_BYTES);
+      ptx::mbar_expect_tx(bar_v, SM::TILE_BYTES);
 #pragma unroll
-    for (int k = 0; k < D / 16; ++k) {
-      const uint32_t off = (k / 4) * 16384 + (k % 4) * 32;          // 4 k-steps per 128 B swizzle atom
-      ptx::mma_ss(tm_S, umma_desc(sQ + off, 16, 1024), umma_desc(sK + off, 16, 1024), idesc, k > 0);
+      for (int hh = 0; hh < SM::HALVES; ++hh) {
+        ptx::tma_load_2d(sQ + hh * 16384, &tm_q, bar_qk, h * D + hh * 64, q0);
+        ptx::tma_load_3d(sK + hh * 16384, &tm_k, bar_qk, hh * 64, kv0, a.layer * a.Hkv + hkv);
+      }
+#pragma unroll
+      for (int hh = 0; hh < SM::HALVES; ++hh)
+        ptx::tma_load_3d(sV + hh * 16384, &tm_v, bar_v, hh * 64, kv0, a.layer * a.Hkv + hkv);
     }
-    ptx::tc_commit(bar_mma);
-  }
-  ptx::mbar_wait(bar_mma, 0, a.err_flag, 2);
-  ptx::tc_fence_after();
+    // stage the mask of this (q tile, kv tile) in shared memory while the TMA loads fly
+    const RowMask rm = row_mask(slot, P);
+    uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + SM::OFF_MASK);
+    __half* smask = reinterpret_cast<__half*>(smem + SM::OFF_MASK);
+    if (DENSE) {
+#pragma unroll 4
+      for (int i = tid; i < TILE_Q * TILE_KV; i += 128) {
+        const int rr = i >> 7, cc = i & 127;
+        __half v = __float2half(0.f);
+        if (q0 + rr < a.n && kv0 + cc < kv_len) v = a.dense_mask[(int64_t)(q0 + rr) * a.mask_ld + kv0 + cc];
+        smask[rr * 132 + cc] = v;
+      }
+    } else if (a.tree_words > 0) {               // thread == row: copy this row's ancestor words
+      const int node = slot - (P - 1);
+      const bool has = node >= 1 && node < a.tree_size;
+#pragma unroll 4
+      for (int w = 0; w < a.tree_words; ++w)
+        sbits[tid * a.tree_words + w] = has ? a.tree_bits[(int64_t)node * a.tree_words + w] : 0u;
+    }
+    __syncthreads();
 
-  // ---- softmax over this tile (thread == row, TMEM lane == row) ---------------------------------------------------
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  const float sc = a.scale * LOG2E;              // work in the log2 domain
-  const uint32_t* my_bits = sbits + tid * a.tree_words;
-  float mx = -INFINITY;
-  uint32_t vis[4];
+    // ---- S = Q K^T ------------------------------------------------------------------------------------------------
+    if (tid == 0) {
+      ptx::mbar_wait_one(bar_qk, 0, a.err_flag, 1);
+      ptx::tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc(TILE_KV, false);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t r[32];
-    ptx::tmem_ld32(tm_S + lane_base + j * 32, r);
-    if (a.dense_mask) {
-      const int rem = kv_len - (kv0 + j * 32);
-      vis[j] = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-#pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if ((vis[j] >> e) & 1u)
-          mx = fmaxf(mx, __uint_as_float(r[e]) * sc + h2f(smask[tid * 132 + j * 32 + e]) * LOG2E);
-    } else {
-      vis[j] = vis_word(rm, kv0 + j * 32, P, kv_len, my_bits, a.tree_words);
-#pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if ((vis[j] >> e) & 1u) mx = fmaxf(mx, __uint_as_float(r[e]) * sc);
+      for (int k = 0; k < D / 16; ++k) {
+        const uint32_t off = (k / 4) * 16384 + (k % 4) * 32;        // 4 k-steps per 128 B swizzle atom
+        ptx::mma_ss(tm_S, umma_desc(sQ + off, 16, 1024), umma_desc(sK + off, 16, 1024), idesc, k > 0);
+      }
+      ptx::tc_commit(bar_mma);
     }
-  }
-  float lsum = 0.f;
-  const float mref = (mx == -INFINITY) ? 0.f : mx;
+    __syncwarp();
+    ptx::mbar_wait(bar_mma, 0, a.err_flag, 2);
+    ptx::tc_fence_after();
+
+    // ---- softmax over this tile -----------------------------------------------------------------------------------
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const float sc = a.scale * LOG2E;            // work in the log2 domain
+    const uint32_t* my_bits = sbits + tid * a.tree_words;
+    const __half* my_mask = smask + tid * 132;
+    uint32_t vis[4];
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tm_S + lane_base + j * 32, r);
+      uint32_t v;
+      if (DENSE) {
+        const int rem = kv_len - (kv0 + j * 32);
+        v = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+      } else {
+        v = vis_word(rm, kv0 + j * 32, P, kv_len, my_bits, a.tree_words);
+      }
+      vis[j] = v;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t r[32];
-    ptx::tmem_ld32(tm_S + lane_base + j * 32, r);
-    uint32_t pk[16];
-#pragma unroll
-    for (int e = 0; e < 32; e += 2) {
-      float p0 = 0.f, p1 = 0.f;
-      if ((vis[j] >> e) & 1u) {
+      for (int e = 0; e < 32; ++e) {
         float s = __uint_as_float(r[e]) * sc;
-        if (a.dense_mask) s += h2f(smask[tid * 132 + j * 32 + e]) * LOG2E;
-        p0 = exp2f(s - mref);
+        if (DENSE) s += h2f(my_mask[j * 32 + e]) * LOG2E;
+        mx = fmaxf(mx, ((v >> e) & 1u) ? s : -INFINITY);
       }
-      if ((vis[j] >> (e + 1)) & 1u) {
-        float s = __uint_as_float(r[e + 1]) * sc;
-        if (a.dense_mask) s += h2f(smask[tid * 132 + j * 32 + e + 1]) * LOG2E;
-        p1 = exp2f(s - mref);
-      }
-      const __half2 hp = __floats2half2_rn(p0, p1);           // P is fp16 like the reference's attn_weights
-      lsum += __low2float(hp) + __high2float(hp);
-      pk[e / 2] = *reinterpret_cast<const uint32_t*>(&hp);
     }
-    ptx::tmem_st16(tm_P + lane_base + j * 16, pk);
-  }
-  ptx::tmem_st_wait();
-  ptx::tc_fence_before();
-  __syncthreads();
-
-  // ---- O = P V ----------------------------------------------------------------------------------------------------
-  if (tid == 0) {
-    ptx::tc_fence_after();
-    ptx::mbar_wait_one(bar_v, 0, a.err_flag, 3);
-    ptx::tc_fence_after();
-    constexpr uint32_t idesc = umma_idesc(D, true);
-    const uint32_t lbo = (a.debug_flags & 1) ? 1024u : 16384u;   // stride between 64-wide D halves
-    const uint32_t sbo = (a.debug_flags & 1) ? 16384u : 1024u;   // stride between 8-key groups
+    const float mref = (mx == -INFINITY) ? 0.f : mx;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tm_S + lane_base + j * 32, r);
+      const uint32_t v = vis[j];
+      uint32_t pk[16];
 #pragma unroll
-    for (int k = 0; k < TILE_KV / 16; ++k)
-      ptx::mma_ts(tm_O, tm_P + k * 8, umma_desc(sV + k * 2048, lbo, sbo), idesc, k > 0);
-    ptx::tc_commit(bar_mma);
-  }
-  ptx::mbar_wait(bar_mma, 1, a.err_flag, 4);
-  ptx::tc_fence_after();
+      for (int e = 0; e < 32; e += 2) {
+        float s0 = __uint_as_float(r[e]) * sc, s1 = __uint_as_float(r[e + 1]) * sc;
+        if (DENSE) {
+          s0 += h2f(my_mask[j * 32 + e]) * LOG2E;
+          s1 += h2f(my_mask[j * 32 + e + 1]) * LOG2E;
+        }
+        const float p0 = ((v >> e) & 1u) ? exp2f(s0 - mref) : 0.f;
+        const float p1 = ((v >> (e + 1)) & 1u) ? exp2f(s1 - mref) : 0.f;
+        const __half2 hp = __floats2half2_rn(p0, p1);           // P is fp16 like the reference's attn_weights
+        lsum += __low2float(hp) + __high2float(hp);
+        pk[e / 2] = *reinterpret_cast<const uint32_t*>(&hp);
+      }
+      ptx::tmem_st16(tm_P + lane_base + j * 16, pk);
+    }
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    __syncthreads();
 
-  if (row < a.n) {
-    ws_ml[0] = mx;       // log2-domain running max
-    ws_ml[1] = lsum;
-  }
+    // ---- O = P V --------------------------------------------------------------------------------------------------
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      ptx::mbar_wait_one(bar_v, 0, a.err_flag, 3);
+      ptx::tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc(D, true);
 #pragma unroll
-  for (int j = 0; j < D / 32; ++j) {
-    uint32_t r[32];
-    ptx::tmem_ld32(tm_O + lane_base + j * 32, r);
-    if (row < a.n) {
+      for (int k = 0; k < TILE_KV / 16; ++k)      // V: MN-major, 16 KB between the 64-wide D halves, 1 KB per 8 keys
+        ptx::mma_ts(tm_O, tm_P + k * 8, umma_desc(sV + k * 2048, 16384, 1024), idesc, k > 0);
+      ptx::tc_commit(bar_mma);
+    }
+    __syncwarp();
+    ptx::mbar_wait(bar_mma, 1, a.err_flag, 4);
+    ptx::tc_fence_after();
+
+    // publish the partial (unnormalised fp32 O, log2-domain max, sum) in this CTA's shared memory
+#pragma unroll 1
+    for (int j = 0; j < D / 32; ++j) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tm_O + lane_base + j * 32, r);
 #pragma unroll
       for (int e = 0; e < 32; e += 4)
-        *reinterpret_cast<uint4*>(ws_o + j * 32 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+        *reinterpret_cast<uint4*>(sO + tid * SM::O_STRIDE + j * 32 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+  }
+  sML[tid] = make_float2(mx, lsum);
+
+  // ---- split-KV reduction across the cluster through distributed shared memory --------------------------------------
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  {
+    constexpr int CPR = D / 4;                   // float4 chunks per row
+    constexpr int RPW = 32 / CPR;                // rows a warp covers at once (1 for D=128, 2 for D=64)
+    const int sub = lane / CPR, cc = lane % CPR;
+    // rows of the tile are dealt round-robin to the Z CTAs, then to the 4 warps; each warp handles UNR rows at a time so
+    // that 2*UNR independent DSMEM loads are in flight per split (the loop is latency-, not bandwidth-bound)
+    constexpr int UNR = 4;
+    const int stride = Z * 4 * RPW;
+#pragma unroll 1
+    for (int r0 = split + Z * (warp * RPW + sub); r0 < TILE_Q; r0 += stride * UNR) {
+      float mm[UNR], den[UNR];
+      float4 acc[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) { mm[u] = -INFINITY; den[u] = 0.f; acc[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll 1
+      for (int s = 0; s < nsplit; ++s) {
+        const float2* pml = cluster.map_shared_rank(sML, s);
+        const float* po = cluster.map_shared_rank(sO, s);
+        float2 ml[UNR];
+        float4 o[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int rr = min(r0 + u * stride, TILE_Q - 1);
+          ml[u] = pml[rr];
+          o[u] = *reinterpret_cast<const float4*>(po + rr * SM::O_STRIDE + cc * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          if (ml[u].x == -INFINITY) continue;
+          const float mn = fmaxf(mm[u], ml[u].x);
+          const float c0 = exp2f(mm[u] - mn), f = exp2f(ml[u].x - mn);   // exp2f(-inf) = 0 on the first hit
+          acc[u].x = acc[u].x * c0 + f * o[u].x; acc[u].y = acc[u].y * c0 + f * o[u].y;
+          acc[u].z = acc[u].z * c0 + f * o[u].z; acc[u].w = acc[u].w * c0 + f * o[u].w;
+          den[u] = den[u] * c0 + f * ml[u].y;
+          mm[u] = mn;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int rr = r0 + u * stride;
+        if (rr >= TILE_Q || q0 + rr >= a.n) continue;
+        const float inv = den[u] > 0.f ? 1.f / den[u] : 0.f;
+        const __half2 lo = __floats2half2_rn(acc[u].x * inv, acc[u].y * inv);
+        const __half2 hi = __floats2half2_rn(acc[u].z * inv, acc[u].w * inv);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(a.out + (int64_t)(q0 + rr) * (a.H * D) + h * D + cc * 4) = pk;
+      }
     }
   }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
-}
-
-// combine split-KV partials: grid (n, H), D threads
-template <int D>
-__global__ void __launch_bounds__(D) tree_attn_combine_kernel(AttnArgs a) {
-  const int r = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
-  const int P = a.state ? a.state[ST_P] : a.prefix_len_host;
-  const int kv_len = (a.state ? (P - 1) : 0) + a.kv_end;
-  const int nsplit = (kv_len + TILE_KV - 1) / TILE_KV;
-  float mm = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, a.ws_ml[(((int64_t)s * a.H + h) * a.n_pad + r) * 2]);
-  float num = 0.f, den = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const int64_t o = ((int64_t)s * a.H + h) * a.n_pad + r;
-    const float m = a.ws_ml[o * 2];
-    if (m == -INFINITY) continue;
-    const float f = exp2f(m - mm);
-    num += f * a.ws_o[o * D + d];
-    den += f * a.ws_ml[o * 2 + 1];
-  }
-  a.out[(int64_t)r * (a.H * D) + h * D + d] = f2h(den > 0.f ? num / den : 0.f);
+  // peers may still be reading this CTA's shared memory: execution barrier only (no memory ordering needed)
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
 
 }  // namespace sq
@@ -550,7 +589,7 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
 extern "C" int64_t sq_attn_workspace_bytes(int n_max, int H, int D, int M) {
   const int64_t n_pad = ((n_max + TILE_Q - 1) / TILE_Q) * TILE_Q;
   const int64_t splits = (M + TILE_KV - 1) / TILE_KV;
-  return splits * H * n_pad * (D + 2) * 4 + 256;
+  return splits * H * n_pad * (D + 2) * 4 + 256 + (int64_t)H * (n_pad / TILE_Q) * 4;
 }
 
 extern "C" int sq_attn_plan_create(sq_attn_plan** plan, const sq_half* q, int ld, int n_max, int H, int Hkv, int D,
@@ -570,9 +609,10 @@ extern "C" int sq_attn_plan_create(sq_attn_plan** plan, const sq_half* q, int ld
   p->ws_o = (float*)workspace;
   p->ws_ml = p->ws_o + (int64_t)p->splits_max * H * p->n_pad * D;
   p->err_flag = (int*)(p->ws_ml + (int64_t)p->splits_max * H * p->n_pad * 2);
+  p->counters = p->err_flag + 64;
   const char* dbg = getenv("SQ_ATTN_DEBUG");
   p->debug_flags = dbg ? atoi(dbg) : 0;
-  cudaMemset(p->err_flag, 0, sizeof(int));
+  cudaMemset(p->err_flag, 0, 256 + (size_t)H * (p->n_pad / TILE_Q) * 4);
   {
     cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)n_max};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
@@ -610,18 +650,30 @@ static int launch_attn(sq_attn_plan* p, AttnArgs& a, int impl, cudaStream_t st) 
     SQ_CHECK_LAUNCH("sq_tree_attn(simt)");
     return SQ_OK;
   }
-  static bool attr_set = false;
   constexpr int smem = TcSmem<D>::TOTAL + 1024;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tree_attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  auto kern = a.dense_mask ? tree_attn_tc_kernel<D, true> : tree_attn_tc_kernel<D, false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[a.dense_mask ? 1 : 0]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("sq_tree_attn: smem attr: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
-    attr_set = true;
+    attr_set[a.dense_mask ? 1 : 0] = true;
   }
   const int q_tiles = (a.n + TILE_Q - 1) / TILE_Q;
-  tree_attn_tc_kernel<D><<<dim3(a.H, q_tiles, p->splits_max), 128, smem, st>>>(p->tm_q, p->tm_k, p->tm_v, a);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(a.H, q_tiles, p->splits_max);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;     // the KV splits of one (head, q tile) form a cluster
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = p->splits_max;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p->tm_q, p->tm_k, p->tm_v, a);
+  if (e != cudaSuccess) { set_error("sq_tree_attn(tc): launch failed: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
   SQ_CHECK_LAUNCH("sq_tree_attn(tc)");
-  tree_attn_combine_kernel<D><<<dim3(a.n, a.H), D, 0, st>>>(a);
-  SQ_CHECK_LAUNCH("sq_tree_attn(combine)");
   return SQ_OK;
 }
 
@@ -632,6 +684,7 @@ extern "C" int sq_tree_attn(sq_attn_plan* plan, int layer, int n, const int32_t*
   SQ_CHECK_ARG(n >= 0 && n <= plan->n_max, "sq_tree_attn: n=%d exceeds plan n_max=%d", n, plan->n_max);
   SQ_CHECK_ARG(layer >= 0 && layer < plan->L, "sq_tree_attn: bad layer %d", layer);
   SQ_CHECK_ARG(tree_words <= 32, "sq_tree_attn: tree_size > 1024 unsupported");
+  SQ_CHECK_ARG(plan->splits_max <= 8, "sq_tree_attn: max_length > 1024 unsupported (8 KV splits)");
   SQ_CHECK_ARG(state != nullptr || kv_end <= plan->M, "sq_tree_attn: kv_end %d > M %d", kv_end, plan->M);
   if (n == 0) return SQ_OK;
   AttnArgs a;
@@ -644,7 +697,7 @@ extern "C" int sq_tree_attn(sq_attn_plan* plan, int layer, int n, const int32_t*
   a.dense_mask = (const __half*)dense_mask; a.mask_ld = mask_ld;
   a.tree_bits = tree_bits; a.tree_words = tree_bits ? tree_words : 0; a.tree_size = tree_bits ? tree_size : 0;
   a.scale = 1.0f / sqrtf((float)plan->D);
-  a.debug_flags = plan->debug_flags; a.err_flag = plan->err_flag;
+  a.debug_flags = plan->debug_flags; a.err_flag = plan->err_flag; a.counters = plan->counters;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->D == 64) return launch_attn<64>(plan, a, impl, st);
   return launch_attn<128>(plan, a, impl, st);

@@ -84,37 +84,43 @@ __global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// grid (n rows, H + 2*Hkv heads); D/2 threads: thread i handles the rotation pair (i, i + D/2).
-__global__ void rope_kv_append_kernel(__half* __restrict__ qkv, int ld, int H, int Hkv, int D,
-                                      const __half* __restrict__ cosc, const __half* __restrict__ sinc,
-                                      const int64_t* __restrict__ position_ids, const int64_t* __restrict__ storage_ids,
-                                      const int32_t* __restrict__ state, int n0, __half* __restrict__ k_layer,
-                                      __half* __restrict__ v_layer, int M) {
-  const int r = blockIdx.x, head = blockIdx.y;
+// One CTA (256 threads) per row.  Work items: for every q/k head and every 16-byte chunk c of the first half of the
+// head, rotate the pair (chunk c, chunk c + D/16) -> two 16-byte loads, two stores; then copy the V heads.
+__global__ void __launch_bounds__(256) rope_kv_append_kernel(
+    __half* __restrict__ qkv, int ld, int H, int Hkv, int D, const __half* __restrict__ cosc,
+    const __half* __restrict__ sinc, const int64_t* __restrict__ position_ids, const int64_t* __restrict__ storage_ids,
+    const int32_t* __restrict__ state, int n0, __half* __restrict__ k_layer, __half* __restrict__ v_layer, int M) {
+  const int r = blockIdx.x;
   const int base = row_base(state, n0);
   const int64_t pos = position_ids[base + r];
   const int64_t slot = storage_ids[base + r];
-  __half* row = qkv + (int64_t)r * ld + (int64_t)head * D;
-  const int i = threadIdx.x, half_d = D / 2;
-  if (head < H + Hkv) {
-    const float x1 = h2f(row[i]), x2 = h2f(row[i + half_d]);
-    const float c1 = h2f(cosc[pos * D + i]), c2 = h2f(cosc[pos * D + i + half_d]);
-    const float s1 = h2f(sinc[pos * D + i]), s2 = h2f(sinc[pos * D + i + half_d]);
-    // q*cos + rotate_half(q)*sin, each op rounded to fp16 (rotate_half = cat(-x2, x1))
-    const __half o1 = f2h(rnd16(x1 * c1) + rnd16(-x2 * s1));
-    const __half o2 = f2h(rnd16(x2 * c2) + rnd16(x1 * s2));
-    if (head < H) {
-      row[i] = o1;
-      row[i + half_d] = o2;
-    } else {
-      __half* dst = k_layer + ((int64_t)(head - H) * M + slot) * D;
-      dst[i] = o1;
-      dst[i + half_d] = o2;
+  __half* row = qkv + (int64_t)r * ld;
+  const int cph = D / 16;                                   // chunk pairs per head
+  const uint4* cs = reinterpret_cast<const uint4*>(cosc + pos * D);
+  const uint4* sn = reinterpret_cast<const uint4*>(sinc + pos * D);
+  for (int w = threadIdx.x; w < (H + Hkv) * cph; w += blockDim.x) {
+    const int head = w / cph, c = w % cph;
+    uint4* src = reinterpret_cast<uint4*>(row + (int64_t)head * D);
+    Pack8 x1, x2, c1, c2, s1, s2, o1, o2;
+    x1.u = src[c]; x2.u = src[c + cph];
+    c1.u = cs[c]; c2.u = cs[c + cph];
+    s1.u = sn[c]; s2.u = sn[c + cph];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a = h2f(x1.h[e]), b = h2f(x2.h[e]);
+      // q*cos + rotate_half(q)*sin, each op rounded to fp16 (rotate_half = cat(-x2, x1))
+      o1.h[e] = f2h(rnd16(a * h2f(c1.h[e])) + rnd16(-b * h2f(s1.h[e])));
+      o2.h[e] = f2h(rnd16(b * h2f(c2.h[e])) + rnd16(a * h2f(s2.h[e])));
     }
-  } else {
-    __half* dst = v_layer + ((int64_t)(head - H - Hkv) * M + slot) * D;
-    dst[i] = row[i];
-    dst[i + half_d] = row[i + half_d];
+    uint4* dst = (head < H) ? src : reinterpret_cast<uint4*>(k_layer + ((int64_t)(head - H) * M + slot) * D);
+    dst[c] = o1.u;
+    dst[c + cph] = o2.u;
+  }
+  const int cpv = D / 8;
+  for (int w = threadIdx.x; w < Hkv * cpv; w += blockDim.x) {
+    const int head = w / cpv, c = w % cpv;
+    reinterpret_cast<uint4*>(v_layer + ((int64_t)head * M + slot) * D)[c] =
+        reinterpret_cast<const uint4*>(row + (int64_t)(H + Hkv + head) * D)[c];
   }
 }
 
@@ -171,10 +177,9 @@ extern "C" int sq_silu_mul(const sq_half* gate_up, sq_half* out, int n, int inte
 extern "C" int sq_rope_kv_append(sq_half* qkv, int ld, int H, int Hkv, int D, const sq_half* cos, const sq_half* sin,
                                  const int64_t* position_ids, const int64_t* storage_ids, const int32_t* state, int n0,
                                  int n, sq_half* k_layer, sq_half* v_layer, int M, void* stream) {
-  SQ_CHECK_ARG(D % 2 == 0 && D <= 2048, "sq_rope_kv_append: bad head dim %d", D);
+  SQ_CHECK_ARG(D % 16 == 0 && ld % 8 == 0, "sq_rope_kv_append: head dim %d / pitch %d must be multiples of 16 / 8", D, ld);
   if (n == 0) return SQ_OK;
-  dim3 grid(n, H + 2 * Hkv);
-  rope_kv_append_kernel<<<grid, D / 2, 0, (cudaStream_t)stream>>>((__half*)qkv, ld, H, Hkv, D, (const __half*)cos,
+  rope_kv_append_kernel<<<n, 256, 0, (cudaStream_t)stream>>>((__half*)qkv, ld, H, Hkv, D, (const __half*)cos,
                                                                  (const __half*)sin, position_ids, storage_ids, state,
                                                                  n0, (__half*)k_layer, (__half*)v_layer, M);
   SQ_CHECK_LAUNCH("sq_rope_kv_append");

@@ -1,0 +1,96 @@
+"""Target tensor parallelism on real GPUs (needs >= 2 devices; skipped otherwise): a TP-2 decode driven through
+sequoia_b200.tp (NCCL broadcasts + 2 allreduces per layer, captured in CUDA graphs) must reproduce the single-GPU
+decode of the same models: target logits within fp16 allreduce-order noise, identical accept lengths / tokens on the
+first iterations."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import cases
+    from sequoia_b200.engine import GraphInferenceEngine, GraphInferenceEngineTG
+    from sequoia_b200.tp import TPFollower, attach_tp, stop_followers
+    from sequoia_b200.tree import SpecTree
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    grp = dist.group.WORLD
+    gm = cases.load_growmap("L40_growmaps/8x8-tree.pt")
+    M, plen, iters = 256, 100, 4
+    dcfg, dw = cases.model_weights("draft")
+    tcfg, tw = cases.model_weights("target_gqa")                   # H=4, Hkv=2 -> shards of 2 q heads + 1 kv head
+    target_tp = GraphInferenceEngineTG(M, {"config": tcfg, "state_dict": tw}, device=dev, tp_group=grp)
+    if rank != 0:
+        TPFollower(target_tp, gm, False, M, dev, grp).serve()
+        dist.destroy_process_group()
+        return
+    try:
+        draft = GraphInferenceEngine(M, {"config": dcfg, "state_dict": dw}, device=dev)
+        draft2 = GraphInferenceEngine(M, {"config": dcfg, "state_dict": dw}, device=dev)
+        target_1 = GraphInferenceEngineTG(M, {"config": tcfg, "state_dict": tw}, device=dev)
+        attach_tp(draft, target_tp, grp)
+        prompt = cases.make_prompt(25, plen).to(dev)
+        buf = lambda: dict(attn_mask=torch.full((M, M), torch.finfo(torch.float16).min, dtype=torch.float16, device=dev),
+                           sequence=torch.arange(M, device=dev).unsqueeze(-1), new_tokens_buffer=torch.zeros(M, device=dev).long(),
+                           parents_buffer=torch.zeros(M, device=dev).long(), position_ids=torch.zeros(M, device=dev).long())
+        noise = torch.empty(iters, cases.V, dtype=torch.float16).exponential_(1.0, generator=torch.Generator().manual_seed(5)).to(dev)
+        trees = []
+        for d, t in ((draft, target_tp), (draft2, target_1)):
+            torch.manual_seed(17)
+            tr = SpecTree(prefix=prompt, device=dev, temperature=0.6, top_p=1.0, draft_model_engine=d, target_model_engine=t,
+                          max_length=M, max_target_seq=M, grow_map=gm, **buf())
+            tr.rt.external_noise = noise
+            trees.append(tr)
+        res = []
+        for it in range(iters):
+            outs = []
+            for tr in trees:
+                tr.construct_grow_map()
+                v, a, _, term = tr.verify()
+                outs.append((v.clone(), a, term, tr.rt.target_logits.float().clone()))
+            (v0, a0, t0, l0), (v1, a1, t1, l1) = outs
+            rel = ((l0 - l1).abs().max() / l1.abs().max()).item()
+            res.append((it, a0 == a1 and t0 == t1 and torch.equal(v0, v1), rel))
+            if not res[-1][1]:
+                break
+        q.put(res)
+    finally:
+        stop_followers(grp, dev)
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_tp2_decode_matches_single_gpu():
+    import torch.multiprocessing as mp
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = q.get(timeout=600)
+    [p.join(120) for p in procs]
+    assert len(res) >= 1
+    for it, same, rel in res:
+        assert rel < 5e-3, f"iter {it}: TP-2 target logits differ from TP-1 by {rel} (relative to max |logit|)"
+    assert res[0][1], "first iteration: TP-2 accept length / tokens differ from single GPU"
+    assert sum(1 for r in res if r[1]) >= 2, f"TP-2 decode forked too early: {res}"
