@@ -117,13 +117,19 @@ def run_b200(args):
 
     def barrier():
         if world > 1:
-            dist.barrier()
+            target._tp_driver.barrier()      # follower ranks are slaved to rank 0: sync + barrier through the control op
         torch.cuda.synchronize()
+
+    def finish():
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            os._exit(0)                      # NCCL communicators captured in CUDA graphs: skip the slow teardown
 
     if rank != 0:
         # follower ranks: target shard only, driven by rank 0's broadcasts
         TPFollower(target, grow_map, greedy, M, dev, tp_group).serve()
-        dist.destroy_process_group()
+        finish()
         return
     draft = GraphInferenceEngine(M, f"random-init:{dname}:1", device=dev)
     if world > 1:
@@ -249,8 +255,7 @@ def run_b200(args):
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_reference(args.config, max_seconds=25.0, max_iters=3)
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def _timeit(fn, iters=20, warm=3, reps=5):

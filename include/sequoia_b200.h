@@ -93,6 +93,9 @@ int sq_attn_plan_create(sq_attn_plan** plan, const sq_half* q, int ld, int n_max
 int sq_attn_plan_destroy(sq_attn_plan* plan);
 /* Synchronous: returns the watchdog word of the plan (0 = no tensor-core / TMA wait ever timed out). */
 int sq_attn_plan_error(sq_attn_plan* plan);
+/* Debug: with SQ_ATTN_TIMING=1 the kernel records clock64() phase stamps of CTA (head 0, q tile 0, split s) at
+ * host_out[s*16 + k] (128 values); SQ_ERR_UNSUPPORTED otherwise. */
+int sq_attn_plan_debug_times(sq_attn_plan* plan, long long* host_out);
 
 /* Attention of n query rows (slots base..base+n-1) of `layer` against cache slots [0, kv_len).
  *   kv_len = (state ? state[P]-1 : 0) + kv_end          (device-driven when state != NULL)

@@ -34,6 +34,7 @@ struct sq_attn_plan {
   int debug_flags;
   int* err_flag;  // device word set by a watchdog timeout
   int* counters;  // [H][n_pad/128] split arrival counters
+  long long* dbg; // phase timestamps (SQ_ATTN_TIMING=1)
   CUtensorMap tm_q, tm_k, tm_v;
 };
 
@@ -62,7 +63,8 @@ struct AttnArgs {
   float scale;
   int debug_flags;
   int* err_flag;
-  int* counters;           // [H][q_tiles] arrival counters of the split-KV CTAs (self-resetting)
+  int* counters;           // (unused by the cluster kernel)
+  long long* dbg;          // optional phase timestamps (SQ_ATTN_TIMING=1): [split][16] clock64 values of CTA (0,0,split)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -299,40 +301,57 @@ struct TcSmem {
   static constexpr int OFF_V = 2 * TILE_BYTES;
   static constexpr int OFF_MASK = 3 * TILE_BYTES;       // 128 x 132 halfs (dense) or 128 x tree_words u32 (bits)
   static constexpr int MASK_BYTES = 128 * 132 * 2;
-  static constexpr int OFF_ML = OFF_MASK + MASK_BYTES;  // per-row (max, sum) of this split: 128 x float2
-  static constexpr int OFF_BAR = OFF_ML + 1024;         // 3 mbarriers + tmem ptr
-  static constexpr int TOTAL = OFF_BAR + 64;
-  // after the second MMA the Q/K/V tiles are dead: the fp32 partial O (128 x (D+4)) is published there for the
-  // cluster-wide split-KV reduction through distributed shared memory
-  static constexpr int O_STRIDE = D + 4;                // floats; +4 keeps the row-per-thread float4 stores conflict-free
-  static_assert(128 * O_STRIDE * 4 <= 3 * TILE_BYTES, "partial O must fit in the dead Q/K/V tiles");
+  static constexpr int OFF_X = OFF_MASK + MASK_BYTES;   // 2 x 128 floats row max + 2 x 128 floats row sum (column halves)
+  static constexpr int OFF_BAR = OFF_X + 2048;          // 3 mbarriers + tmem ptr
+  // Split-KV reduction buffers, written REMOTELY by the peer CTAs of the cluster (push model), so they may not alias
+  // the Q/K/V tiles: row r of the tile is owned by CTA (r % Z); slot [src split][r / Z] holds that split's partial.
+  static constexpr int O_STRIDE = D + 4;                // floats
+  static constexpr int R_ROWS = 128 + 8;                // Z * ceil(128 / Z) <= 136 for Z <= 8
+  static constexpr int OFF_RML = OFF_BAR + 64;          // R_ROWS x float2 (log2-domain max, sum)
+  static constexpr int OFF_R = OFF_RML + R_ROWS * 8;    // R_ROWS x O_STRIDE floats
+  static constexpr int TOTAL = OFF_R + R_ROWS * O_STRIDE * 4;
 };
 
+#define SQ_STAMP(k) do { if (a.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.dbg[split * 16 + (k)] = clock64(); } while (0)
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+
 // impl 0.  grid (H, q_tiles, Z) launched as thread-block clusters (1,1,Z), Z = ceil(M/128) <= 8: the CTAs of one
-// cluster are the KV splits of one (head, q tile).  128 threads, thread == query row == TMEM lane.
-// The loops over 32-column TMEM chunks are deliberately NOT unrolled: every instruction of this kernel runs once per
-// CTA, so code size (instruction-fetch latency) matters more than ILP.
+// cluster are the KV splits of one (head, q tile).  256 threads: warp w covers TMEM lanes (query rows) 32*(w%4).. and
+// the column half w/4 of S / P / O.  Loops over 32-column TMEM chunks are deliberately NOT unrolled: every instruction
+// runs once per CTA, so code size (instruction fetch) matters more than ILP.
 template <int D, bool DENSE>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
     tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, AttnArgs a) {
   using SM = TcSmem<D>;
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16 B aligned: re-align to 1024 B for SWIZZLE_128B (same offset in every CTA)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the __shared__ array itself, so the compiler keeps the shared address space: LDS/STS, not LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int h = blockIdx.x, qt = blockIdx.y, split = blockIdx.z, Z = gridDim.z;
   const int hkv = h / (a.H / a.Hkv);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hf = warp >> 2;                      // column half handled by this thread
+  const int trow = (warp & 3) * 32 + lane;       // tile row == TMEM lane
   const int P = a.state ? a.state[ST_P] : a.prefix_len_host;
   const int base = a.state ? (P - 1) : 0;
   const int kv_len = base + a.kv_end;
   const int kv0 = split * TILE_KV;
   const int q0 = qt * TILE_Q;
-  const int row = q0 + tid;                      // this thread's query row (TMEM lane tid)
-  const int slot = base + a.n0 + row;
+  const int slot = base + a.n0 + q0 + trow;
   const int nsplit = (kv_len + TILE_KV - 1) / TILE_KV;
+  const int rpc = (TILE_Q + Z - 1) / Z;          // rows owned per CTA
 
   bool active = kv0 < kv_len;
   if (active && !DENSE) {                        // whole tile masked for every row of this q tile?
@@ -340,9 +359,12 @@ __global__ void __launch_bounds__(128, 1)
     const int max_vis = (last_slot >= P) ? (kv_len - 1) : min(last_slot, P - 1);
     active = kv0 <= max_vis;
   }
-  float* sO = reinterpret_cast<float*>(smem);
-  float2* sML = reinterpret_cast<float2*>(smem + SM::OFF_ML);
-  float mx = -INFINITY, lsum = 0.f;
+  float* sxmax = reinterpret_cast<float*>(smem + SM::OFF_X);          // [2][128]
+  float* sxsum = sxmax + 256;                                         // [2][128]
+  const uint32_t sR_local = ptx::smem_u32(smem + SM::OFF_R), sRML_local = ptx::smem_u32(smem + SM::OFF_RML);
+  const uint32_t owner = (uint32_t)(trow % Z);
+  const int lrow = trow / Z;                     // row index inside the owner's buffers
+  SQ_STAMP(0);
 
   if (active) {
     const uint32_t sQ = ptx::smem_u32(smem + SM::OFF_Q), sK = ptx::smem_u32(smem + SM::OFF_K),
@@ -354,19 +376,7 @@ __global__ void __launch_bounds__(128, 1)
       ptx::mbar_init(bar_v, 1);
       ptx::mbar_init(bar_mma, 1);
       ptx::fence_barrier_init();
-    }
-    if (warp == 0) {
-      ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 256);
-      ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem = *tmem_ptr_smem;
-    const uint32_t tm_S = tmem;                  // 128 fp32 columns
-    const uint32_t tm_P = tmem;                  // 64 columns (fp16 pairs), aliases S
-    const uint32_t tm_O = tmem + 128;            // D fp32 columns
-    if (tid == 0) {
+      // kick the TMA loads off before anything else: their latency is the longest pole of this kernel
       ptx::mbar_expect_tx(bar_qk, 2 * SM::TILE_BYTES);
       ptx::mbar_expect_tx(bar_v, SM::TILE_BYTES);
 #pragma unroll
@@ -378,30 +388,43 @@ __global__ void __launch_bounds__(128, 1)
       for (int hh = 0; hh < SM::HALVES; ++hh)
         ptx::tma_load_3d(sV + hh * 16384, &tm_v, bar_v, hh * 64, kv0, a.layer * a.Hkv + hkv);
     }
+    __syncwarp();
+    if (warp == 0) {
+      ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 512);
+      ptx::tmem_relinquish();
+    }
     // stage the mask of this (q tile, kv tile) in shared memory while the TMA loads fly
     const RowMask rm = row_mask(slot, P);
     uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + SM::OFF_MASK);
     __half* smask = reinterpret_cast<__half*>(smem + SM::OFF_MASK);
     if (DENSE) {
 #pragma unroll 4
-      for (int i = tid; i < TILE_Q * TILE_KV; i += 128) {
+      for (int i = tid; i < TILE_Q * TILE_KV; i += 256) {
         const int rr = i >> 7, cc = i & 127;
         __half v = __float2half(0.f);
         if (q0 + rr < a.n && kv0 + cc < kv_len) v = a.dense_mask[(int64_t)(q0 + rr) * a.mask_ld + kv0 + cc];
         smask[rr * 132 + cc] = v;
       }
-    } else if (a.tree_words > 0) {               // thread == row: copy this row's ancestor words
+    } else if (a.tree_words > 0 && hf == 0) {    // one thread per row copies that row's ancestor words
       const int node = slot - (P - 1);
       const bool has = node >= 1 && node < a.tree_size;
 #pragma unroll 4
       for (int w = 0; w < a.tree_words; ++w)
-        sbits[tid * a.tree_words + w] = has ? a.tree_bits[(int64_t)node * a.tree_words + w] : 0u;
+        sbits[trow * a.tree_words + w] = has ? a.tree_bits[(int64_t)node * a.tree_words + w] : 0u;
     }
+    ptx::tc_fence_before();
     __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+    SQ_STAMP(1);
+    const uint32_t tm_S = tmem;                  // 128 fp32 columns
+    const uint32_t tm_O = tmem + 128;            // D fp32 columns
+    const uint32_t tm_P = tmem + 256;            // 64 columns of fp16 pairs (A operand of the second MMA)
 
     // ---- S = Q K^T ------------------------------------------------------------------------------------------------
     if (tid == 0) {
       ptx::mbar_wait_one(bar_qk, 0, a.err_flag, 1);
+      SQ_STAMP(2);
       ptx::tc_fence_after();
       constexpr uint32_t idesc = umma_idesc(TILE_KV, false);
 #pragma unroll
@@ -414,17 +437,18 @@ __global__ void __launch_bounds__(128, 1)
     __syncwarp();
     ptx::mbar_wait(bar_mma, 0, a.err_flag, 2);
     ptx::tc_fence_after();
+    SQ_STAMP(3);
 
-    // ---- softmax over this tile -----------------------------------------------------------------------------------
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ---- softmax over this tile: thread = (row, column half) ---------------------------------------------------------
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float sc = a.scale * LOG2E;            // work in the log2 domain
-    const uint32_t* my_bits = sbits + tid * a.tree_words;
-    const __half* my_mask = smask + tid * 132;
-    uint32_t vis[4];
+    const uint32_t* my_bits = sbits + trow * a.tree_words;
+    const __half* my_mask = smask + trow * 132;
+    uint32_t vis[2];
+    float mxl = -INFINITY;                       // max of the RAW scores (scale > 0 is applied once afterwards)
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      uint32_t r[32];
-      ptx::tmem_ld32(tm_S + lane_base + j * 32, r);
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = hf * 2 + jj;
       uint32_t v;
       if (DENSE) {
         const int rem = kv_len - (kv0 + j * 32);
@@ -432,37 +456,71 @@ __global__ void __launch_bounds__(128, 1)
       } else {
         v = vis_word(rm, kv0 + j * 32, P, kv_len, my_bits, a.tree_words);
       }
-      vis[j] = v;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        float s = __uint_as_float(r[e]) * sc;
-        if (DENSE) s += h2f(my_mask[j * 32 + e]) * LOG2E;
-        mx = fmaxf(mx, ((v >> e) & 1u) ? s : -INFINITY);
-      }
-    }
-    const float mref = (mx == -INFINITY) ? 0.f : mx;
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+      vis[jj] = v;
+      // tcgen05.ld is .sync.aligned: the decision to skip it must be warp-uniform
+      if (__all_sync(0xffffffffu, v == 0u)) continue;          // nothing visible in this chunk for the whole warp
+      const bool all_full = __all_sync(0xffffffffu, v == 0xFFFFFFFFu);
       uint32_t r[32];
       ptx::tmem_ld32(tm_S + lane_base + j * 32, r);
-      const uint32_t v = vis[j];
-      uint32_t pk[16];
+      if (DENSE) {
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        float s0 = __uint_as_float(r[e]) * sc, s1 = __uint_as_float(r[e + 1]) * sc;
-        if (DENSE) {
-          s0 += h2f(my_mask[j * 32 + e]) * LOG2E;
-          s1 += h2f(my_mask[j * 32 + e + 1]) * LOG2E;
+        for (int e = 0; e < 32; ++e)
+          mxl = fmaxf(mxl, ((v >> e) & 1u) ? __uint_as_float(r[e]) + h2f(my_mask[j * 32 + e]) * (1.f / a.scale) : -INFINITY);
+      } else if (all_full) {                     // fully visible chunk (the whole committed prefix): no bit tests
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mxl = fmaxf(mxl, __uint_as_float(r[e]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mxl = fmaxf(mxl, ((v >> e) & 1u) ? __uint_as_float(r[e]) : -INFINITY);
+      }
+    }
+    sxmax[hf * 128 + trow] = mxl;
+    __syncthreads();
+    const float mx = fmaxf(sxmax[trow], sxmax[128 + trow]) * sc;     // log2-domain row max of this split
+    const float mref = (mx == -INFINITY) ? 0.f : mx;
+    float lsum = 0.f;
+#pragma unroll 1
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = hf * 2 + jj;
+      const uint32_t v = vis[jj];
+      uint32_t pk[16];
+      if (__all_sync(0xffffffffu, v == 0u)) {    // warp-uniform (tcgen05.ld is .sync.aligned)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = 0u;
+      } else {
+        const bool all_full = __all_sync(0xffffffffu, v == 0xFFFFFFFFu);
+        uint32_t r[32];
+        ptx::tmem_ld32(tm_S + lane_base + j * 32, r);
+        if (!DENSE && all_full) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = exp2f(__uint_as_float(r[e]) * sc - mref);
+            const float p1 = exp2f(__uint_as_float(r[e + 1]) * sc - mref);
+            lsum += p0 + p1;
+            const __half2 hp = __floats2half2_rn(p0, p1);
+            pk[e / 2] = *reinterpret_cast<const uint32_t*>(&hp);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float s0 = __uint_as_float(r[e]) * sc, s1 = __uint_as_float(r[e + 1]) * sc;
+            if (DENSE) {
+              s0 += h2f(my_mask[j * 32 + e]) * LOG2E;
+              s1 += h2f(my_mask[j * 32 + e + 1]) * LOG2E;
+            }
+            const float p0 = ((v >> e) & 1u) ? exp2f(s0 - mref) : 0.f;
+            const float p1 = ((v >> (e + 1)) & 1u) ? exp2f(s1 - mref) : 0.f;
+            lsum += p0 + p1;
+            const __half2 hp = __floats2half2_rn(p0, p1);         // P is fp16 like the reference's attn_weights
+            pk[e / 2] = *reinterpret_cast<const uint32_t*>(&hp);
+          }
         }
-        const float p0 = ((v >> e) & 1u) ? exp2f(s0 - mref) : 0.f;
-        const float p1 = ((v >> (e + 1)) & 1u) ? exp2f(s1 - mref) : 0.f;
-        const __half2 hp = __floats2half2_rn(p0, p1);           // P is fp16 like the reference's attn_weights
-        lsum += __low2float(hp) + __high2float(hp);
-        pk[e / 2] = *reinterpret_cast<const uint32_t*>(&hp);
       }
       ptx::tmem_st16(tm_P + lane_base + j * 16, pk);
     }
+    sxsum[hf * 128 + trow] = lsum;
     ptx::tmem_st_wait();
+    SQ_STAMP(4);
     ptx::tc_fence_before();
     __syncthreads();
 
@@ -480,77 +538,89 @@ __global__ void __launch_bounds__(128, 1)
     __syncwarp();
     ptx::mbar_wait(bar_mma, 1, a.err_flag, 4);
     ptx::tc_fence_after();
+    SQ_STAMP(5);
 
-    // publish the partial (unnormalised fp32 O, log2-domain max, sum) in this CTA's shared memory
+    // stage this split's partial O (unnormalised fp32) row-major in the now dead Q/K/V tiles ...
+    float* sO = reinterpret_cast<float*>(smem);
+    {
 #pragma unroll 1
-    for (int j = 0; j < D / 32; ++j) {
-      uint32_t r[32];
-      ptx::tmem_ld32(tm_O + lane_base + j * 32, r);
+      for (int jj = 0; jj < D / 64; ++jj) {
+        const int j = hf * (D / 64) + jj;
+        uint32_t r[32];
+        ptx::tmem_ld32(tm_O + lane_base + j * 32, r);
 #pragma unroll
-      for (int e = 0; e < 32; e += 4)
-        *reinterpret_cast<uint4*>(sO + tid * SM::O_STRIDE + j * 32 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+        for (int e = 0; e < 32; e += 4)
+          *reinterpret_cast<uint4*>(sO + trow * SM::O_STRIDE + j * 32 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+      }
+      if (hf == 0)
+        st_cluster_v2(mapa_u32(sRML_local, owner) + (uint32_t)((split * rpc + lrow) * 8), mx, sxsum[trow] + sxsum[128 + trow]);
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
-  }
-  sML[tid] = make_float2(mx, lsum);
-
-  // ---- split-KV reduction across the cluster through distributed shared memory --------------------------------------
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  {
-    constexpr int CPR = D / 4;                   // float4 chunks per row
-    constexpr int RPW = 32 / CPR;                // rows a warp covers at once (1 for D=128, 2 for D=64)
-    const int sub = lane / CPR, cc = lane % CPR;
-    // rows of the tile are dealt round-robin to the Z CTAs, then to the 4 warps; each warp handles UNR rows at a time so
-    // that 2*UNR independent DSMEM loads are in flight per split (the loop is latency-, not bandwidth-bound)
-    constexpr int UNR = 4;
-    const int stride = Z * 4 * RPW;
-#pragma unroll 1
-    for (int r0 = split + Z * (warp * RPW + sub); r0 < TILE_Q; r0 += stride * UNR) {
-      float mm[UNR], den[UNR];
-      float4 acc[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) { mm[u] = -INFINITY; den[u] = 0.f; acc[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
-#pragma unroll 1
-      for (int s = 0; s < nsplit; ++s) {
-        const float2* pml = cluster.map_shared_rank(sML, s);
-        const float* po = cluster.map_shared_rank(sO, s);
-        float2 ml[UNR];
-        float4 o[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int rr = min(r0 + u * stride, TILE_Q - 1);
-          ml[u] = pml[rr];
-          o[u] = *reinterpret_cast<const float4*>(po + rr * SM::O_STRIDE + cc * 4);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          if (ml[u].x == -INFINITY) continue;
-          const float mn = fmaxf(mm[u], ml[u].x);
-          const float c0 = exp2f(mm[u] - mn), f = exp2f(ml[u].x - mn);   // exp2f(-inf) = 0 on the first hit
-          acc[u].x = acc[u].x * c0 + f * o[u].x; acc[u].y = acc[u].y * c0 + f * o[u].y;
-          acc[u].z = acc[u].z * c0 + f * o[u].z; acc[u].w = acc[u].w * c0 + f * o[u].w;
-          den[u] = den[u] * c0 + f * ml[u].y;
-          mm[u] = mn;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int rr = r0 + u * stride;
-        if (rr >= TILE_Q || q0 + rr >= a.n) continue;
-        const float inv = den[u] > 0.f ? 1.f / den[u] : 0.f;
-        const __half2 lo = __floats2half2_rn(acc[u].x * inv, acc[u].y * inv);
-        const __half2 hi = __floats2half2_rn(acc[u].z * inv, acc[u].w * inv);
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(a.out + (int64_t)(q0 + rr) * (a.H * D) + h * D + cc * 4) = pk;
+    if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+    SQ_STAMP(10);
+    // ... and push every row to the CTA that owns it: one warp moves one row (512 B contiguous remote store)
+    {
+      constexpr int CPR = D / 4, RPW = 32 / CPR;
+      const int sub = lane / CPR, cc = lane % CPR;
+#pragma unroll 4
+      for (int rr = warp * RPW + sub; rr < TILE_Q; rr += 8 * RPW) {
+        const uint4 val = *reinterpret_cast<const uint4*>(sO + rr * SM::O_STRIDE + cc * 4);
+        const uint32_t dst = mapa_u32(sR_local, (uint32_t)(rr % Z)) + (uint32_t)(((split * rpc + rr / Z) * SM::O_STRIDE + cc * 4) * 4);
+        st_cluster_v4(dst, val.x, val.y, val.z, val.w);
       }
     }
+    SQ_STAMP(6);
+  } else if (split < nsplit && hf == 0) {
+    st_cluster_v2(mapa_u32(sRML_local, owner) + (uint32_t)((split * rpc + lrow) * 8), -INFINITY, 0.f);
   }
-  // peers may still be reading this CTA's shared memory: execution barrier only (no memory ordering needed)
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+
+  // ---- split-KV reduction: every CTA normalises the rows it owns, from its OWN shared memory -------------------------
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  SQ_STAMP(7);
+  {
+    const float2* sRML = reinterpret_cast<const float2*>(smem + SM::OFF_RML);
+    const float* sR = reinterpret_cast<const float*>(smem + SM::OFF_R);
+    float* wts = reinterpret_cast<float*>(smem + SM::OFF_MASK);       // [rpc][8] normalised split weights (mask is dead)
+    // phase 1: one thread per owned row -> weight of every split: 2^(m_s - m) / sum_s 2^(m_s - m) l_s
+    if (tid < rpc) {
+      float mm = -INFINITY;
+      for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, sRML[s * rpc + tid].x);
+      float den = 0.f;
+      for (int s = 0; s < nsplit; ++s) {
+        const float2 ml = sRML[s * rpc + tid];
+        const float f = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - mm);
+        wts[tid * 8 + s] = f;
+        den += f * ml.y;
+      }
+      const float inv = den > 0.f ? 1.f / den : 0.f;
+      for (int s = 0; s < nsplit; ++s) wts[tid * 8 + s] *= inv;
+    }
+    __syncthreads();
+    SQ_STAMP(9);
+    // phase 2: flat, dependency-free weighted sum over (row, 4-column chunk)
+    constexpr int CPR = D / 4;
+#pragma unroll 2
+    for (int i = tid; i < rpc * CPR; i += 256) {
+      const int lr = i / CPR, cc = i % CPR;
+      const int rr = lr * Z + split;             // tile row owned by this CTA
+      if (rr >= TILE_Q || q0 + rr >= a.n) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < nsplit; ++s) {
+        const float w = wts[lr * 8 + s];
+        if (w == 0.f) continue;                  // masked / empty split: its O slot was never written
+        const float4 o = (a.debug_flags & 4) ? make_float4(1.f, 2.f, 3.f, 4.f)
+                                             : *reinterpret_cast<const float4*>(sR + (s * rpc + lr) * SM::O_STRIDE + cc * 4);
+        acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
+      }
+      const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      if (!(a.debug_flags & 2)) *reinterpret_cast<uint2*>(a.out + (int64_t)(q0 + rr) * (a.H * D) + h * D + cc * 4) = pk;
+    }
+  }
+  SQ_STAMP(8);
 }
 
 }  // namespace sq
@@ -589,7 +659,7 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
 extern "C" int64_t sq_attn_workspace_bytes(int n_max, int H, int D, int M) {
   const int64_t n_pad = ((n_max + TILE_Q - 1) / TILE_Q) * TILE_Q;
   const int64_t splits = (M + TILE_KV - 1) / TILE_KV;
-  return splits * H * n_pad * (D + 2) * 4 + 256 + (int64_t)H * (n_pad / TILE_Q) * 4;
+  return splits * H * n_pad * (D + 2) * 4 + 256 + (int64_t)H * (n_pad / TILE_Q) * 4 + 8 * 16 * 8 + 64;
 }
 
 extern "C" int sq_attn_plan_create(sq_attn_plan** plan, const sq_half* q, int ld, int n_max, int H, int Hkv, int D,
@@ -610,6 +680,12 @@ extern "C" int sq_attn_plan_create(sq_attn_plan** plan, const sq_half* q, int ld
   p->ws_ml = p->ws_o + (int64_t)p->splits_max * H * p->n_pad * D;
   p->err_flag = (int*)(p->ws_ml + (int64_t)p->splits_max * H * p->n_pad * 2);
   p->counters = p->err_flag + 64;
+  {
+    uintptr_t d = (uintptr_t)(p->counters + (int64_t)H * (p->n_pad / TILE_Q));
+    d = (d + 15) & ~(uintptr_t)15;
+    const char* tenv = getenv("SQ_ATTN_TIMING");
+    p->dbg = (tenv && atoi(tenv)) ? (long long*)d : nullptr;
+  }
   const char* dbg = getenv("SQ_ATTN_DEBUG");
   p->debug_flags = dbg ? atoi(dbg) : 0;
   cudaMemset(p->err_flag, 0, 256 + (size_t)H * (p->n_pad / TILE_Q) * 4);
@@ -637,6 +713,12 @@ extern "C" int sq_attn_plan_destroy(sq_attn_plan* plan) {
   return SQ_OK;
 }
 
+extern "C" int sq_attn_plan_debug_times(sq_attn_plan* plan, long long* host_out) {
+  if (!plan->dbg) return SQ_ERR_UNSUPPORTED;
+  cudaMemcpy(host_out, plan->dbg, 8 * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  return SQ_OK;
+}
+
 extern "C" int sq_attn_plan_error(sq_attn_plan* plan) {
   int v = 0;
   cudaMemcpy(&v, plan->err_flag, sizeof(int), cudaMemcpyDeviceToHost);
@@ -661,7 +743,7 @@ static int launch_attn(sq_attn_plan* p, AttnArgs& a, int impl, cudaStream_t st) 
   const int q_tiles = (a.n + TILE_Q - 1) / TILE_Q;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(a.H, q_tiles, p->splits_max);
-  cfg.blockDim = dim3(128);
+  cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -697,7 +779,7 @@ extern "C" int sq_tree_attn(sq_attn_plan* plan, int layer, int n, const int32_t*
   a.dense_mask = (const __half*)dense_mask; a.mask_ld = mask_ld;
   a.tree_bits = tree_bits; a.tree_words = tree_bits ? tree_words : 0; a.tree_size = tree_bits ? tree_size : 0;
   a.scale = 1.0f / sqrtf((float)plan->D);
-  a.debug_flags = plan->debug_flags; a.err_flag = plan->err_flag; a.counters = plan->counters;
+  a.debug_flags = plan->debug_flags; a.err_flag = plan->err_flag; a.counters = plan->counters; a.dbg = plan->dbg;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->D == 64) return launch_attn<64>(plan, a, impl, st);
   return launch_attn<128>(plan, a, impl, st);

@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 from .tree import _Static
 
-OP_STOP, OP_STEADY, OP_FIRST, OP_CLEAR = 0, 1, 2, 3
+OP_STOP, OP_STEADY, OP_FIRST, OP_CLEAR, OP_BARRIER = 0, 1, 2, 3, 4
 
 
 class TPDriver:
@@ -35,6 +35,13 @@ class TPDriver:
     def send_ctrl(self, op: int, a: int = 0, b: int = 0):
         self.ctrl.copy_(torch.tensor([op, a, b, 0], dtype=torch.int64), non_blocking=False)
         dist.broadcast(self.ctrl, self.src, group=self.group)
+
+    def barrier(self):
+        """Device-synchronise every rank and meet in a collective barrier (bench.py brackets its timed region with it)."""
+        self.send_ctrl(OP_BARRIER)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        dist.barrier(group=self.group)
 
     def bcast_inputs(self, rt):
         dist.broadcast(rt.tokens, self.src, group=self.group)
@@ -115,7 +122,11 @@ class TPFollower:
                 if self.device.type == "cuda":
                     torch.cuda.synchronize()
                 return
-            if op == OP_CLEAR:
+            if op == OP_BARRIER:
+                if self.device.type == "cuda":
+                    torch.cuda.synchronize()
+                dist.barrier(group=self.group)
+            elif op == OP_CLEAR:
                 self.target.clear_kv()
             elif op == OP_FIRST:
                 self._first(a, b)

@@ -42,8 +42,7 @@ def _worker(rank, world, port, q):
     target_tp = GraphInferenceEngineTG(M, {"config": tcfg, "state_dict": tw}, device=dev, tp_group=grp)
     if rank != 0:
         TPFollower(target_tp, gm, False, M, dev, grp).serve()
-        dist.destroy_process_group()
-        return
+        os._exit(0)
     try:
         draft = GraphInferenceEngine(M, {"config": dcfg, "state_dict": dw}, device=dev)
         draft2 = GraphInferenceEngine(M, {"config": dcfg, "state_dict": dw}, device=dev)
@@ -74,9 +73,11 @@ def _worker(rank, world, port, q):
             if not res[-1][1]:
                 break
         q.put(res)
+        q.close()
+        q.join_thread()
     finally:
         stop_followers(grp, dev)
-        dist.destroy_process_group()
+        os._exit(0)                                  # skip the slow NCCL / CUDA-graph teardown
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -88,7 +89,8 @@ def test_tp2_decode_matches_single_gpu():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
     res = q.get(timeout=600)
-    [p.join(120) for p in procs]
+    [p.join(60) for p in procs]
+    [p.kill() for p in procs if p.is_alive()]
     assert len(res) >= 1
     for it, same, rel in res:
         assert rel < 5e-3, f"iter {it}: TP-2 target logits differ from TP-1 by {rel} (relative to max |logit|)"

@@ -38,3 +38,18 @@ for _ in range(5):
     g.replay()
 e1.record(); e1.synchronize()
 print("attention us/launch:", e0.elapsed_time(e1) / (10 * L) * 1e3, "plan error", plan.error())
+
+if os.environ.get("SQ_ATTN_TIMING"):
+    import ctypes, numpy as np
+    from sequoia_b200 import _lib
+    call(0); torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * 128)()
+    rc = _lib.load().sq_attn_plan_debug_times(plan.handle, buf)
+    t = np.array(list(buf)).reshape(8, 16)
+    names = ["start", "alloc+sync", "TMA q,k landed", "MMA1 done", "softmax done", "MMA2 done", "epilogue+dealloc", "cluster sync 1", "reduction", "cluster sync 2"]
+    for s_ in range(3):
+        row = t[s_]
+        order = [0, 1, 2, 3, 4, 5, 10, 6, 7, 9, 8]
+        nm = {0: "start", 1: "alloc+mask+sync", 2: "TMA q,k landed", 3: "MMA1 done", 4: "softmax done", 5: "MMA2 done",
+              10: "O staged+dealloc", 6: "pushed", 7: "cluster sync", 9: "weights", 8: "reduced"}
+        print("split", s_, " ".join(f"{nm[k]}:+{int(row[k]-row[0])}" for k in order))
