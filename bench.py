@@ -355,6 +355,32 @@ def micro_kernels(draft, target, tree, grow_map):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def pick_cpu_threads():
+    """torch's fp16 CPU GEMM does not scale to every core count (128 threads were 10x slower than 8 on the build box):
+    try powers of two up to os.cpu_count() on one 7B-shaped linear and keep the fastest, i.e. all the threads the
+    reference's CPU path can actually use."""
+    n = os.cpu_count() or 1
+    x = torch.randn(128, 4096).half()
+    w = torch.randn(4096, 4096).half()
+    best, best_t = 1, float("inf")
+    c = 1
+    cands = []
+    while c < n:
+        cands.append(c)
+        c *= 2
+    cands.append(n)
+    for c in cands[-5:]:
+        torch.set_num_threads(c)
+        torch.nn.functional.linear(x, w)
+        t0 = time.time()
+        for _ in range(3):
+            torch.nn.functional.linear(x, w)
+        dt = time.time() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
 def cpu_reference(config, max_seconds, max_iters, warm_iters=1):
     """The reference's algorithm on the host cores: the torch-CPU oracle port (oracle/sequoia_oracle.py) on the same
     shapes.  To keep host init bounded, all target layers alias ONE layer's random weights (identical FLOPs/bytes per
@@ -362,7 +388,7 @@ def cpu_reference(config, max_seconds, max_iters, warm_iters=1):
     from oracle import sequoia_oracle as O
     from sequoia_b200.model import NAMED_CONFIGS
     dname, tname, gm_path, greedy, T, top_p, M, prefix, max_len = CONFIGS[config]
-    ncores = os.cpu_count() or 1
+    ncores = pick_cpu_threads()
     torch.set_num_threads(ncores)
     grow_map = torch.load(os.path.join(ROOT, gm_path))
 
