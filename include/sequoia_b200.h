@@ -158,6 +158,23 @@ int sq_accept_greedy(const int64_t* target_token, const int32_t* succ_off, const
                      const int32_t* depth, int S, int64_t* tokens, int64_t* position_ids, int32_t* accept_idx,
                      int32_t* state, int max_target_seq, void* stream);
 
+/* ---- target tensor parallelism: fused one-shot all-reduce over NVLink peer memory (no reference counterpart) ---- */
+
+/* Peer-mappable device buffers (cudaMalloc + CUDA IPC).  handle64: 64-byte cudaIpcMemHandle_t. */
+int sq_tp_alloc(void** ptr, int64_t bytes);
+int sq_tp_free(void* ptr);
+int sq_tp_ipc_export(void* ptr, uint8_t* handle64);
+int sq_tp_ipc_open(const uint8_t* handle64, void** ptr);
+int sq_tp_ipc_close(void* ptr);
+/* resid += sum_r proj_r ; out = rmsnorm(resid) * weight   for n rows, in ONE kernel on every rank:
+ * replaces NCCL all-reduce + sq_add_rmsnorm after the row-parallel o_proj / down_proj (Llama_modules.py:341,347).
+ * host_proj_ptrs[N]: device pointers to rank 0..N-1's partial output (n_max, hidden) fp16 (own + peer-mapped);
+ * host_flag_ptrs[N]: device pointers to each rank's N-word flag array; epoch: 4 local words (epoch, ticket, error, -).
+ * Every rank must launch the matching call; the partial buffers of consecutive reductions must alternate (A, B). */
+int sq_tp_allreduce_add_rmsnorm(sq_half* resid, const void* const* host_proj_ptrs, void* const* host_flag_ptrs,
+                                uint32_t* epoch, int rank, int N, const sq_half* weight, sq_half* out, int n,
+                                int hidden, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

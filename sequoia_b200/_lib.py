@@ -40,6 +40,12 @@ _SIGNATURES = {
     "sq_argmax_rows": (i32, [vp, i64, i32, i32, vp, vp]),
     "sq_accept_stochastic": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, i32, vp]),
     "sq_accept_greedy": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]),
+    "sq_tp_alloc": (i32, [C.POINTER(vp), i64]),
+    "sq_tp_free": (i32, [vp]),
+    "sq_tp_ipc_export": (i32, [vp, vp]),
+    "sq_tp_ipc_open": (i32, [vp, C.POINTER(vp)]),
+    "sq_tp_ipc_close": (i32, [vp]),
+    "sq_tp_allreduce_add_rmsnorm": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,0 +1,172 @@
+// Tensor-parallel target forward: ONE kernel = one-shot all-reduce over NVLink peer memory + residual add + RMSNorm.
+//
+// Under target TP every row-parallel GEMM (o_proj, down_proj) is followed by a sum over the ranks and
+// then by `hidden += x; normed = rmsnorm(hidden)`.  Instead of NCCL allreduce + sq_add_rmsnorm (two launches, ~20 us
+// for a 1 MiB payload), each rank's kernel reads the partial GEMM outputs of ALL ranks straight from their HBM through
+// NVLink/NVSwitch peer mappings (CUDA IPC), sums them in fp32 in a fixed rank order (bit-identical on every rank),
+// and continues with the residual add and the norm.  Synchronisation is a per-launch epoch handshake through flag
+// words in peer memory (st.release.sys / ld.acquire.sys); the epoch lives on the device, so the kernel is CUDA-graph
+// replayable.  The partial buffers alternate (A for o_proj, B for down_proj): the handshake of the NEXT reduction
+// proves that every peer has finished reading the previous contents of a buffer before it is overwritten.
+#include <cstring>
+
+#include "sq_common.cuh"
+
+namespace sq {
+
+struct TpArgs {
+  const __half* proj[8];     // partial GEMM outputs of rank 0..N-1 (peer-mapped, same layout (n_max, hidden))
+  uint32_t* flags[8];        // flags[r] = flag array living on rank r (N words; word s is written by rank s)
+  uint32_t* epoch;           // local: [0] epoch of the last completed reduction, [1] CTA ticket, [2] error word
+  int rank, N;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_relaxed_sys_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
+// One CTA (256 threads) per row, hidden <= 256*8*MAXV.
+template <int MAXV>
+__global__ void __launch_bounds__(256) tp_allreduce_add_rmsnorm_kernel(TpArgs t, __half* __restrict__ resid,
+                                                                       const __half* __restrict__ w,
+                                                                       __half* __restrict__ out, int hidden, float eps) {
+  __shared__ float red[8];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const uint32_t e = t.epoch[0] + 1;                         // identical in every CTA: only bumped by the last CTA
+  if (r == 0 && tid < t.N && tid != t.rank) st_release_sys(t.flags[tid] + t.rank, e);   // "my partial is ready"
+  if (tid < t.N && tid != t.rank) {                          // wait until every peer's partial of this epoch is ready
+    const uint32_t* f = t.flags[t.rank] + tid;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(f) - e) < 0) {
+      if (clock64() - t0 > 4000000000LL) { atomicExch(t.epoch + 2, 1u); break; }      // ~2 s: never hang the box
+    }
+  }
+  __syncthreads();
+  const int nvec = hidden / 8;
+  Pack8 v[MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    if (c < nvec) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int s = 0; s < t.N; ++s) {                         // fixed order => every rank computes the same bits
+        Pack8 p;
+        const __half* src = t.proj[s] + (int64_t)r * hidden;
+        if (s == t.rank) p.u = reinterpret_cast<const uint4*>(src)[c];
+        else p.u = ld_relaxed_sys_v4(reinterpret_cast<const uint4*>(src) + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += h2f(p.h[j]);
+      }
+      Pack8 a;
+      a.u = reinterpret_cast<const uint4*>(resid + (int64_t)r * hidden)[c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __half x = f2h(acc[j]);                        // the all-reduced projection output (fp16 like the reference's)
+        v[i].h[j] = f2h(h2f(a.h[j]) + h2f(x));               // residual + x  (fp16 add)
+        const float f = h2f(v[i].h[j]);
+        ss += f * f;
+      }
+      reinterpret_cast<uint4*>(resid + (int64_t)r * hidden)[c] = v[i].u;
+    }
+  }
+  ss = block_sum<8>(ss, red);
+  const float inv = rsqrtf(ss / (float)hidden + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    if (c < nvec) {
+      Pack8 wv, o;
+      wv.u = reinterpret_cast<const uint4*>(w)[c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.h[j] = f2h(h2f(wv.h[j]) * h2f(f2h(h2f(v[i].h[j]) * inv)));
+      reinterpret_cast<uint4*>(out + (int64_t)r * hidden)[c] = o.u;
+    }
+  }
+  // the last CTA to finish publishes the new epoch (all CTAs have read the old one by then)
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t ticket = atomicAdd(t.epoch + 1, 1u);
+    if (ticket == gridDim.x - 1) {
+      t.epoch[1] = 0u;
+      __threadfence();
+      t.epoch[0] = e;
+    }
+  }
+}
+
+}  // namespace sq
+
+using namespace sq;
+
+extern "C" int sq_tp_alloc(void** ptr, int64_t bytes) {
+  cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaMemset(*ptr, 0, (size_t)bytes);
+  if (e != cudaSuccess) { set_error("sq_tp_alloc: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
+  return SQ_OK;
+}
+
+extern "C" int sq_tp_free(void* ptr) {
+  cudaFree(ptr);
+  return SQ_OK;
+}
+
+extern "C" int sq_tp_ipc_export(void* ptr, uint8_t* handle64) {
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) { set_error("sq_tp_ipc_export: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return SQ_OK;
+}
+
+extern "C" int sq_tp_ipc_open(const uint8_t* handle64, void** ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { set_error("sq_tp_ipc_open: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
+  return SQ_OK;
+}
+
+extern "C" int sq_tp_ipc_close(void* ptr) {
+  cudaIpcCloseMemHandle(ptr);
+  return SQ_OK;
+}
+
+extern "C" int sq_tp_allreduce_add_rmsnorm(sq_half* resid, const void* const* host_proj_ptrs,
+                                           void* const* host_flag_ptrs, uint32_t* epoch, int rank, int N,
+                                           const sq_half* weight, sq_half* out, int n, int hidden, float eps,
+                                           void* stream) {
+  SQ_CHECK_ARG(N >= 2 && N <= 8 && rank >= 0 && rank < N, "sq_tp_allreduce_add_rmsnorm: bad rank/N %d/%d", rank, N);
+  SQ_CHECK_ARG(hidden % 8 == 0 && hidden <= 256 * 8 * 8, "sq_tp_allreduce_add_rmsnorm: hidden=%d unsupported", hidden);
+  if (n == 0) return SQ_OK;
+  TpArgs t;
+  for (int i = 0; i < 8; ++i) {
+    t.proj[i] = i < N ? (const __half*)host_proj_ptrs[i] : nullptr;
+    t.flags[i] = i < N ? (uint32_t*)host_flag_ptrs[i] : nullptr;
+  }
+  t.epoch = epoch;
+  t.rank = rank;
+  t.N = N;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nvec = hidden / 8;
+  if (nvec <= 256) tp_allreduce_add_rmsnorm_kernel<1><<<n, 256, 0, st>>>(t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
+  else if (nvec <= 512) tp_allreduce_add_rmsnorm_kernel<2><<<n, 256, 0, st>>>(t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
+  else if (nvec <= 1024) tp_allreduce_add_rmsnorm_kernel<4><<<n, 256, 0, st>>>(t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
+  else tp_allreduce_add_rmsnorm_kernel<8><<<n, 256, 0, st>>>(t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
+  SQ_CHECK_LAUNCH("sq_tp_allreduce_add_rmsnorm");
+  return SQ_OK;
+}

@@ -217,6 +217,12 @@ class LlamaRunner:
         self.k_cache = torch.zeros(self.L, 1, self.Hkv, max_length, D, dtype=F16, device=dev)
         self.v_cache = torch.zeros_like(self.k_cache)
         self.plan = ops.AttnPlan(self.qkv, n, self.H, self.Hkv, D, self.k_cache, self.v_cache, self.attn_out)
+        # TP: the row-parallel GEMMs write into NVLink peer-visible buffers and ONE kernel does all-reduce + residual +
+        # RMSNorm (csrc/sq_tp.cu).  SQ_TP_MODE=nccl keeps torch.distributed.all_reduce + sq_add_rmsnorm (baseline).
+        self.peer = None
+        if self.tp.size > 1 and os.environ.get("SQ_TP_MODE", "fused") == "fused":
+            from .peer import PeerBuffers
+            self.peer = PeerBuffers(tp_group, self.device, n, h)
         self.attn_impl = int(os.environ.get("SQ_ATTN_IMPL", "0"))
 
     def weight_bytes(self) -> int:
@@ -245,6 +251,15 @@ class LlamaRunner:
             ops.tree_attn(self.plan, l, n, state=state, n0=n0, kv_end=kv_end, prefix_len=prefix_len,
                           dense_mask=dense_mask, mask_ld=mask_ld, tree_bits=tree_bits, tree_words=tree_words,
                           tree_size=tree_size, impl=self.attn_impl)
+            nxt = self.layers[l + 1]["ln1"] if l + 1 < self.L else self.norm
+            if self.peer is not None:
+                torch.mm(self.attn_out[:n], ly["wo"].t(), out=self.peer.buf[0][:n])
+                self.peer.allreduce_add_rmsnorm(0, self.hidden, ly["ln2"], self.normed, n, self.eps)
+                torch.mm(nrm, ly["wgu"].t(), out=self.gate_up[:n])
+                ops.silu_mul(self.gate_up, self.act, n)
+                torch.mm(self.act[:n], ly["wd"].t(), out=self.peer.buf[1][:n])
+                self.peer.allreduce_add_rmsnorm(1, self.hidden, nxt, self.normed, n, self.eps)
+                continue
             torch.mm(self.attn_out[:n], ly["wo"].t(), out=self.proj[:n])
             self.tp.all_reduce(self.proj[:n])
             ops.add_rmsnorm(self.hidden, self.proj, ly["ln2"], self.normed, n, self.eps)
@@ -252,7 +267,6 @@ class LlamaRunner:
             ops.silu_mul(self.gate_up, self.act, n)
             torch.mm(self.act[:n], ly["wd"].t(), out=self.proj[:n])
             self.tp.all_reduce(self.proj[:n])
-            nxt = self.layers[l + 1]["ln1"] if l + 1 < self.L else self.norm
             ops.add_rmsnorm(self.hidden, self.proj, nxt, self.normed, n, self.eps)
         if skip_lm_head:                               # TP follower ranks: only rank 0 consumes logits
             return None

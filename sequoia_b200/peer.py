@@ -1,0 +1,69 @@
+"""NVLink peer-memory buffers for the fused TP all-reduce kernel (csrc/sq_tp.cu).
+
+Each rank cudaMalloc's one block [partial A | partial B | flags | epoch], exports it with CUDA IPC, and maps every
+peer's block (cudaIpcOpenMemHandle, peer access over NVLink / NVSwitch).  torch sees the two partial buffers as ordinary
+fp16 tensors (zero-copy via __cuda_array_interface__), so the row-parallel GEMMs write their outputs straight into
+peer-visible memory with `torch.mm(..., out=...)`."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+class _CudaArray:
+    def __init__(self, address: int, shape, typestr="<f2"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (address, False), "version": 2}
+
+
+class PeerBuffers:
+    FLAG_BYTES = 1024
+
+    def __init__(self, group, device, n_max: int, hidden: int):
+        lib = _lib.load()
+        self.group, self.device = group, torch.device(device)
+        self.N, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        assert 2 <= self.N <= 8
+        self.n_max, self.hidden = n_max, hidden
+        part = n_max * hidden * 2
+        total = 2 * part + 2 * self.FLAG_BYTES
+        base = C.c_void_p()
+        check(lib.sq_tp_alloc(C.byref(base), total), "sq_tp_alloc")
+        self.base = base.value
+        handle = (C.c_uint8 * 64)()
+        check(lib.sq_tp_ipc_export(base, handle), "sq_tp_ipc_export")
+        handles = [None] * self.N
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.bases = []
+        self._opened = []
+        for r in range(self.N):
+            if r == self.rank:
+                self.bases.append(self.base)
+                continue
+            p = C.c_void_p()
+            h = (C.c_uint8 * 64).from_buffer_copy(handles[r])
+            check(lib.sq_tp_ipc_open(h, C.byref(p)), "sq_tp_ipc_open")
+            self.bases.append(p.value)
+            self._opened.append(p.value)
+        arr = C.c_void_p * 8
+        self.proj_ptrs = [arr(*[(b + w * part) for b in self.bases] + [None] * (8 - self.N)) for w in range(2)]
+        self.flag_ptrs = arr(*[(b + 2 * part) for b in self.bases] + [None] * (8 - self.N))
+        self.epoch_ptr = self.base + 2 * part + self.FLAG_BYTES
+        self.buf = [torch.as_tensor(_CudaArray(self.base + w * part, (n_max, hidden)), device=self.device) for w in range(2)]
+        assert self.buf[0].data_ptr() == self.base and self.buf[0].dtype == torch.float16
+        dist.barrier(group=group)                      # every rank has mapped every peer before the first kernel runs
+
+    def allreduce_add_rmsnorm(self, which: int, resid: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, n: int,
+                              eps: float):
+        """resid += sum over ranks of partial buffer `which`; out = rmsnorm(resid) * weight  (one kernel per rank)."""
+        check(_lib.load().sq_tp_allreduce_add_rmsnorm(ptr(resid), self.proj_ptrs[which], self.flag_ptrs, self.epoch_ptr,
+                                                      self.rank, self.N, ptr(weight), ptr(out), n, self.hidden, eps,
+                                                      stream_ptr()), "sq_tp_allreduce_add_rmsnorm")
+
+    def error(self) -> int:
+        t = torch.as_tensor(_CudaArray(self.epoch_ptr, (4,), "<i4"), device=self.device)
+        return int(t[2])

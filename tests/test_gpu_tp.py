@@ -72,6 +72,7 @@ def _worker(rank, world, port, q):
             res.append((it, a0 == a1 and t0 == t1 and torch.equal(v0, v1), rel))
             if not res[-1][1]:
                 break
+        res.append(("peer_error", target_tp.engine.runner.peer.error() if target_tp.engine.runner.peer else 0, 0.0))
         q.put(res)
         q.close()
         q.join_thread()
@@ -91,7 +92,9 @@ def test_tp2_decode_matches_single_gpu():
     res = q.get(timeout=600)
     [p.join(60) for p in procs]
     [p.kill() for p in procs if p.is_alive()]
-    assert len(res) >= 1
+    assert len(res) >= 2
+    tag, err, _ = res.pop()
+    assert tag == "peer_error" and err == 0, "fused all-reduce handshake timed out"
     for it, same, rel in res:
         assert rel < 5e-3, f"iter {it}: TP-2 target logits differ from TP-1 by {rel} (relative to max |logit|)"
     assert res[0][1], "first iteration: TP-2 accept length / tokens differ from single GPU"
