@@ -158,6 +158,19 @@ int sq_accept_greedy(const int64_t* target_token, const int32_t* succ_off, const
                      const int32_t* depth, int S, int64_t* tokens, int64_t* position_ids, int32_t* accept_idx,
                      int32_t* state, int max_target_seq, void* stream);
 
+/* ---- weight-streaming GEMM for <= 128 rows (nn.Linear, Llama_modules.py:108-110,138,270-272; Llama_model.py:213) ---- */
+
+/* C[n, N] = A[n, K] * W[N, K]^T, fp16 in / fp32 accumulate / fp16 out, n <= 128.  A: (n_max, lda), W: (N, K) row-major
+ * (the nn.Linear weight as stored), C: (n_max, ldc).  K % 64 == 0, N % 128 == 0.  Plans hold the TMA descriptors; create
+ * once per (activation buffer, weight, output buffer), run inside graphs.  err_flag: optional device word set by the
+ * pipeline watchdog.  Larger n (prefill) stays on cuBLASLt. */
+typedef struct sq_gemm_plan sq_gemm_plan;
+int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N, int K,
+                        sq_half* c, int ldc, int* err_flag);
+int sq_gemm_plan_destroy(sq_gemm_plan* plan);
+int sq_gemm_plan_info(sq_gemm_plan* plan, int* bn, int* split, int* stages);
+int sq_gemm_run(sq_gemm_plan* plan, int n, void* stream);
+
 /* ---- target tensor parallelism: fused one-shot all-reduce over NVLink peer memory (no reference counterpart) ---- */
 
 /* Peer-mappable device buffers (cudaMalloc + CUDA IPC).  handle64: 64-byte cudaIpcMemHandle_t. */

@@ -1,0 +1,289 @@
+// Weight-streaming GEMM for the tree-verify shapes:  C[n <= 128, N] = A[n, K] * W[N, K]^T   (fp16 in, fp32 accumulate
+// in tensor memory, fp16 out) -- nn.Linear of the target / draft forward (Engine/Llama_modules.py:108-110,138,270-272,
+// Llama_model.py:213) for at most 128 rows.  With 128 rows every weight byte is used once: the kernel is a pure HBM
+// stream (roofline = weight bytes / HBM bandwidth), so the design goal is bytes in flight, not FLOPs:
+//   * one CTA per 128- or 256-wide slice of N (one wave on 148 SMs), warp-specialised: 1 TMA producer lane, 1 MMA
+//     issuer lane, 4 epilogue warps; a 4-6 stage mbarrier ring of (A 128x64, W BNx64) SWIZZLE_128B tiles keeps
+//     128-192 KB per SM in flight; tcgen05.mma kind::f16 M=128 N=BN K=16, accumulator in TMEM;
+//   * narrow outputs (o_proj / down_proj: N = hidden = 32 slices only) are split along K over a thread-block cluster
+//     (1, SPLIT, 1): each CTA streams 1/SPLIT of K, pushes its fp32 partial rows into the shared memory of the row's
+//     owner CTA (st.shared::cluster), one cluster barrier, owners add in a fixed order and store fp16.
+#include <cstdio>
+#include <cstdlib>
+
+#include "sq_common.cuh"
+#include "sq_ptx.cuh"
+
+struct sq_gemm_plan {
+  CUtensorMap tm_a, tm_w;
+  __half* c;
+  int ldc, n_max, N, K, bn, split, stages;
+  int* err_flag;
+};
+
+namespace sq {
+
+struct GemmArgs {
+  __half* c;
+  int ldc, n, N, K, kb_per_split;   // kb = 64-wide K blocks handled by one CTA
+  int* err_flag;
+};
+
+constexpr int G_BK = 64;
+constexpr int G_THREADS = 192;       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+
+template <int BN, int STAGES, int SPLIT>
+struct GemmSmem {
+  static constexpr int A_BYTES = 128 * 128;            // 128 rows x 64 halfs
+  static constexpr int W_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr int OFF_BAR = STAGES * STAGE_BYTES; // full[STAGES], empty[STAGES], tmem_full, tmem ptr
+  static constexpr int OFF_RED = OFF_BAR + 256;        // split-K: SPLIT slots x (128/SPLIT rows) x (BN+4) floats
+  static constexpr int R_STRIDE = BN + 4;
+  static constexpr int RED_BYTES = SPLIT > 1 ? 128 * R_STRIDE * 4 : 0;
+  static constexpr int TOTAL = OFF_RED + RED_BYTES;
+};
+
+template <int BN, int STAGES, int SPLIT>
+__global__ void __launch_bounds__(G_THREADS, 1)
+    gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, GemmArgs g) {
+  using SM = GemmSmem<BN, STAGES, SPLIT>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN;
+  const int ks = blockIdx.y;                               // K split index == rank in the cluster
+  const int kb0 = ks * g.kb_per_split;
+  const int nkb = g.kb_per_split;
+  const uint32_t s_base = ptx::smem_u32(smem);
+  const uint32_t bar_full = s_base + SM::OFF_BAR, bar_empty = bar_full + 8 * STAGES, bar_tmem = bar_empty + 8 * STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + 16 * STAGES + 8);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    ptx::mbar_init(bar_tmem, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait_one(bar_empty + 8 * stage, phase ^ 1, g.err_flag, 11);     // slot free (fresh barrier passes)
+        const uint32_t sa = s_base + stage * SM::STAGE_BYTES, sw = sa + SM::A_BYTES;
+        ptx::mbar_expect_tx(bar_full + 8 * stage, SM::STAGE_BYTES);
+        ptx::tma_load_2d(sa, &tm_a, bar_full + 8 * stage, (kb0 + kb) * G_BK, 0);
+        ptx::tma_load_2d(sw, &tm_w, bar_full + 8 * stage, (kb0 + kb) * G_BK, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BN, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait_one(bar_full + 8 * stage, phase, g.err_flag, 12);           // TMA bytes have landed
+        ptx::tc_fence_after();
+        const uint32_t sa = s_base + stage * SM::STAGE_BYTES, sw = sa + SM::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < G_BK / 16; ++k)
+          ptx::mma_ss(tmem, umma_desc(sa + k * 32, 16, 1024), umma_desc(sw + k * 32, 16, 1024), idesc, (kb | k) != 0);
+        ptx::tc_commit(bar_empty + 8 * stage);                                     // frees the slot when the MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::tc_commit(bar_tmem);                                                    // accumulator complete
+    }
+  } else {
+    // ===== epilogue: 4 warps, thread == output row == TMEM lane =====
+    const int lg = warp & 3;                                // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;
+    ptx::mbar_wait(bar_tmem, 0, g.err_flag, 13);
+    ptx::tc_fence_after();
+    const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
+    if (SPLIT == 1) {
+      __half* crow = g.c + (int64_t)row * g.ldc + n0;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem + lane_base + j * 32, r);
+        if (row < g.n) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            Pack8 o;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o.h[q] = f2h(__uint_as_float(r[e + q]));
+            *reinterpret_cast<uint4*>(crow + j * 32 + e) = o.u;
+          }
+        }
+      }
+    } else {
+      // push this K-split's fp32 partial row to the CTA that owns the row (rows dealt in blocks of 128/SPLIT)
+      constexpr int RPC = 128 / SPLIT;
+      const uint32_t owner = (uint32_t)(row / RPC);
+      uint32_t dst;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(s_base + SM::OFF_RED), "r"(owner));
+      dst += (uint32_t)((ks * RPC + row % RPC) * SM::R_STRIDE * 4);
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem + lane_base + j * 32, r);
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (j * 32 + e) * 4), "r"(r[e]),
+                       "r"(r[e + 1]), "r"(r[e + 2]), "r"(r[e + 3])
+                       : "memory");
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, BN);
+
+  if (SPLIT > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // owner CTA ks reduces rows [ks*RPC, (ks+1)*RPC): sum of the SPLIT slots in split order, fp16 out
+    constexpr int RPC = 128 / SPLIT;
+    constexpr int CPR = BN / 4;
+    const float* red = reinterpret_cast<const float*>(smem + SM::OFF_RED);
+    for (int i = tid; i < RPC * CPR; i += G_THREADS) {
+      const int lr = i / CPR, cc = i % CPR;
+      const int row = ks * RPC + lr;
+      if (row >= g.n) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < SPLIT; ++s) {
+        const float4 o = *reinterpret_cast<const float4*>(red + (s * RPC + lr) * SM::R_STRIDE + cc * 4);
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+      const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(g.c + (int64_t)row * g.ldc + n0 + cc * 4) = pk;
+    }
+  }
+}
+
+}  // namespace sq
+
+using namespace sq;
+
+typedef CUresult (*PFN_tmapEncodeTiledG)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                     uint32_t box_inner, uint32_t box_outer, CUtensorMapL2promotion prom) {
+  static PFN_tmapEncodeTiledG fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiledG)p;
+  }
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable"); return SQ_ERR_CUDA; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return SQ_ERR_CUDA; }
+  return SQ_OK;
+}
+
+extern "C" int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N,
+                                   int K, sq_half* c, int ldc, int* err_flag) {
+  SQ_CHECK_ARG(plan && a && w && c, "sq_gemm_plan_create: null pointer");
+  SQ_CHECK_ARG(K % 64 == 0 && N % 128 == 0 && lda % 8 == 0 && ldc % 8 == 0, "sq_gemm_plan_create: K %% 64, N %% 128");
+  sq_gemm_plan* p = new sq_gemm_plan();
+  p->c = (__half*)c; p->ldc = ldc; p->n_max = n_max; p->N = N; p->K = K; p->err_flag = err_flag;
+  const int tiles128 = N / 128;
+  const int kb = K / 64;
+  // one wave on 148 SMs: wide outputs use 256-wide tiles when that fits one wave; narrow outputs split K over a cluster
+  if (tiles128 > 148 && N % 256 == 0 && N / 256 <= 148) { p->bn = 256; p->split = 1; p->stages = 4; }
+  else if (tiles128 <= 37 && kb % 4 == 0) { p->bn = 128; p->split = 4; p->stages = 4; }
+  else if (tiles128 <= 74 && kb % 2 == 0) { p->bn = 128; p->split = 2; p->stages = 4; }
+  else { p->bn = 128; p->split = 1; p->stages = 6; }
+  const char* force = getenv("SQ_GEMM_FORCE");          // debugging: "bn,split"
+  if (force) {
+    int fb = 0, fs = 0;
+    if (sscanf(force, "%d,%d", &fb, &fs) == 2 && (fb == 128 || fb == 256) && (fs == 1 || fs == 2 || fs == 4) &&
+        N % fb == 0 && kb % fs == 0) { p->bn = fb; p->split = fs; p->stages = (fb == 128 && fs == 1) ? 6 : 4; }
+  }
+  int rc = encode_2d(&p->tm_a, a, (uint64_t)K, (uint64_t)n_max, (uint64_t)lda * 2, 64, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  if (!rc) rc = encode_2d(&p->tm_w, w, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 64, (uint32_t)p->bn, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc) { delete p; return rc; }
+  *plan = p;
+  return SQ_OK;
+}
+
+extern "C" int sq_gemm_plan_destroy(sq_gemm_plan* plan) {
+  delete plan;
+  return SQ_OK;
+}
+
+template <int BN, int STAGES, int SPLIT>
+static int launch_gemm(sq_gemm_plan* p, GemmArgs& g, cudaStream_t st) {
+  using SM = GemmSmem<BN, STAGES, SPLIT>;
+  constexpr int smem = SM::TOTAL + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("sq_gemm: smem attr: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p->N / BN, SPLIT, 1);
+  cfg.blockDim = dim3(G_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1;
+  at[0].val.clusterDim.y = SPLIT;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, STAGES, SPLIT>, p->tm_a, p->tm_w, g);
+  if (e != cudaSuccess) { set_error("sq_gemm: launch failed: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
+  SQ_CHECK_LAUNCH("sq_gemm");
+  return SQ_OK;
+}
+
+extern "C" int sq_gemm_run(sq_gemm_plan* plan, int n, void* stream) {
+  SQ_CHECK_ARG(plan != nullptr, "sq_gemm_run: null plan");
+  SQ_CHECK_ARG(n >= 0 && n <= 128 && n <= plan->n_max, "sq_gemm_run: n=%d must be <= 128 (and <= n_max)", n);
+  if (n == 0) return SQ_OK;
+  GemmArgs g;
+  g.c = plan->c; g.ldc = plan->ldc; g.n = n; g.N = plan->N; g.K = plan->K;
+  g.kb_per_split = plan->K / 64 / plan->split;
+  g.err_flag = plan->err_flag;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->bn == 256) return launch_gemm<256, 4, 1>(plan, g, st);
+  if (plan->split == 4) return launch_gemm<128, 4, 4>(plan, g, st);
+  if (plan->split == 2) return launch_gemm<128, 4, 2>(plan, g, st);
+  return launch_gemm<128, 6, 1>(plan, g, st);
+}
+
+extern "C" int sq_gemm_plan_info(sq_gemm_plan* plan, int* bn, int* split, int* stages) {
+  *bn = plan->bn; *split = plan->split; *stages = plan->stages;
+  return SQ_OK;
+}

@@ -219,11 +219,38 @@ class LlamaRunner:
         self.plan = ops.AttnPlan(self.qkv, n, self.H, self.Hkv, D, self.k_cache, self.v_cache, self.attn_out)
         # TP: the row-parallel GEMMs write into NVLink peer-visible buffers and ONE kernel does all-reduce + residual +
         # RMSNorm (csrc/sq_tp.cu).  SQ_TP_MODE=nccl keeps torch.distributed.all_reduce + sq_add_rmsnorm (baseline).
+        # Optional hand-written weight-streaming GEMM (csrc/sq_gemm.cu) for forwards of <= 128 rows.  OFF by default:
+        # in round 1 it is bit-compatible with cuBLASLt but not yet faster, so the dense GEMMs
+        # stay on cuBLASLt as SURVEY.md 2.2 K1 prescribes.  SQ_GEMM=1 turns it on (tests / tuning).
+        self.gemm = None
+        if os.environ.get("SQ_GEMM", "0") == "1":
+            self.gemm_err = torch.zeros(4, dtype=torch.int32, device=dev)
+            self.gemm = []
+            for ly in self.layers:
+                self.gemm.append(dict(qkv=self._plan(self.normed, ly["wqkv"], self.qkv),
+                                      o=self._plan(self.attn_out, ly["wo"], self.proj),
+                                      gu=self._plan(self.normed, ly["wgu"], self.gate_up),
+                                      d=self._plan(self.act, ly["wd"], self.proj)))
         self.peer = None
         if self.tp.size > 1 and os.environ.get("SQ_TP_MODE", "fused") == "fused":
             from .peer import PeerBuffers
             self.peer = PeerBuffers(tp_group, self.device, n, h)
         self.attn_impl = int(os.environ.get("SQ_ATTN_IMPL", "0"))
+
+    def _plan(self, a, w, c):
+        try:
+            return ops.GemmPlan(a, w, c, self.gemm_err)
+        except Exception:
+            return None                                   # shape outside the kernel's tiling (K % 64, N % 128): cuBLASLt
+
+    def _linear(self, l: int, key: str, x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, n: int):
+        """out[:n] = x[:n] @ w.T"""
+        if self.gemm is not None and n <= 128 and self.peer is None:
+            plan = self.gemm[l][key]
+            if plan is not None:
+                plan.run(n)
+                return
+        torch.mm(x[:n], w.t(), out=out[:n])
 
     def weight_bytes(self) -> int:
         b = self.embed.numel() + self.lm_head.numel() + self.norm.numel()
@@ -245,7 +272,7 @@ class LlamaRunner:
         ops.embed_rows(self.embed, tokens, n, self.hidden, state=state, n0=n0)
         ops.rmsnorm(self.hidden, self.layers[0]["ln1"], self.normed, n, self.eps)
         for l, ly in enumerate(self.layers):
-            torch.mm(nrm, ly["wqkv"].t(), out=self.qkv[:n])
+            self._linear(l, "qkv", self.normed, ly["wqkv"], self.qkv, n)
             ops.rope_kv_append(self.qkv, H, Hkv, D, self.cos, self.sin, position_ids, storage_ids, n,
                                self.k_cache[l], self.v_cache[l], M, state=state, n0=n0)
             ops.tree_attn(self.plan, l, n, state=state, n0=n0, kv_end=kv_end, prefix_len=prefix_len,
@@ -260,12 +287,12 @@ class LlamaRunner:
                 torch.mm(self.act[:n], ly["wd"].t(), out=self.peer.buf[1][:n])
                 self.peer.allreduce_add_rmsnorm(1, self.hidden, nxt, self.normed, n, self.eps)
                 continue
-            torch.mm(self.attn_out[:n], ly["wo"].t(), out=self.proj[:n])
+            self._linear(l, "o", self.attn_out, ly["wo"], self.proj, n)
             self.tp.all_reduce(self.proj[:n])
             ops.add_rmsnorm(self.hidden, self.proj, ly["ln2"], self.normed, n, self.eps)
-            torch.mm(nrm, ly["wgu"].t(), out=self.gate_up[:n])
+            self._linear(l, "gu", self.normed, ly["wgu"], self.gate_up, n)
             ops.silu_mul(self.gate_up, self.act, n)
-            torch.mm(self.act[:n], ly["wd"].t(), out=self.proj[:n])
+            self._linear(l, "d", self.act, ly["wd"], self.proj, n)
             self.tp.all_reduce(self.proj[:n])
             ops.add_rmsnorm(self.hidden, self.proj, nxt, self.normed, n, self.eps)
         if skip_lm_head:                               # TP follower ranks: only rank 0 consumes logits

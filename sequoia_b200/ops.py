@@ -142,3 +142,32 @@ def accept_greedy(target_token, succ_off, succ, depth, S, tokens, position_ids, 
     check(_lib.load().sq_accept_greedy(ptr(target_token), ptr(succ_off), ptr(succ), ptr(depth), S, ptr(tokens),
                                        ptr(position_ids), ptr(accept_idx), ptr(state), max_target_seq, stream_ptr()),
           "sq_accept_greedy")
+
+
+class GemmPlan:
+    """C[:n] = A[:n] @ W.T for n <= 128 on the weight-streaming tcgen05 kernel (csrc/sq_gemm.cu)."""
+
+    def __init__(self, a: torch.Tensor, w: torch.Tensor, c: torch.Tensor, err_flag: Optional[torch.Tensor] = None):
+        lib = _lib.load()
+        assert a.dtype == F16 and w.dtype == F16 and c.dtype == F16 and w.is_contiguous()
+        assert a.stride(-1) == 1 and c.stride(-1) == 1 and a.shape[1] == w.shape[1] and c.shape[1] >= w.shape[0]
+        self.handle = C.c_void_p()
+        self._keep = (a, w, c, err_flag)
+        check(lib.sq_gemm_plan_create(C.byref(self.handle), ptr(a), a.stride(0), a.shape[0], ptr(w), w.shape[0], w.shape[1],
+                                      ptr(c), c.stride(0), ptr(err_flag)), "sq_gemm_plan_create")
+
+    def info(self):
+        bn, sp, st = C.c_int(), C.c_int(), C.c_int()
+        _lib.load().sq_gemm_plan_info(self.handle, C.byref(bn), C.byref(sp), C.byref(st))
+        return bn.value, sp.value, st.value
+
+    def run(self, n: int):
+        check(_lib.load().sq_gemm_run(self.handle, n, stream_ptr()), "sq_gemm_run")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().sq_gemm_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

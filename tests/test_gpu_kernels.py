@@ -370,3 +370,24 @@ def test_engine_forward_logits_vs_oracle(kind, key):
         with pytest.raises(ValueError):
             eng.inference(prompt[:4].unsqueeze(0).to(DEV), sto[:4].to(DEV), pos[:4].unsqueeze(0).to(DEV),
                           win[:4, :7][None, None].to(DEV))
+
+
+# ------------------------------------------------------------------------------------------------ weight-streaming GEMM
+@pytest.mark.parametrize("N,K,n,expect", [(1536, 512, 128, None), (768, 3072, 31, None), (6144, 768, 128, None),
+                                          (32000, 768, 19, None), (512, 1024, 1, None)])
+def test_weight_streaming_gemm_matches_cublas(N, K, n, expect):
+    """csrc/sq_gemm.cu (experimental, SQ_GEMM=1) vs an fp32 reference and vs cuBLASLt on the same inputs: same fp32
+    accumulation, one fp16 rounding -> relative error within 1 fp16 ulp of the fp32 result."""
+    g = torch.Generator().manual_seed(N + K)
+    a = (torch.randn(128, K, generator=g) * 0.5).to(F16).to(DEV)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(F16).to(DEV)
+    c = torch.full((128, N), 7.0, dtype=F16, device=DEV)
+    err = torch.zeros(4, dtype=torch.int32, device=DEV)
+    plan = ops().GemmPlan(a, w, c, err)
+    plan.run(n)
+    torch.cuda.synchronize()
+    assert err.tolist() == [0, 0, 0, 0], "GEMM pipeline watchdog fired"
+    ref = a[:n].float() @ w.float().t()
+    nbad, _ = ulp_close(c[:n], ref.to(F16), 1, atol=1e-3)
+    assert nbad == 0, f"plan {plan.info()}: {nbad} outputs beyond 1 fp16 ulp of the fp32 product"
+    assert (c[n:] == 7.0).all(), "rows >= n must not be written"
