@@ -35,7 +35,7 @@ CONFIGS = {
     "c3": ("llama-68m", "llama-2-13b", "L40_growmaps/8x8-tree.pt", False, 0.6, 1.0, 384, 128, 256),
     "c4": ("llama-2-7b", "llama-2-70b", "L40_growmaps/L40-CNN-7b-70b-stochastic.pt", False, 0.6, 1.0, 1024, 128, 256),
 }
-METRIC = "decoded tokens/sec (mean accepted len/step in config), 68m->7B Llama tree speculative decoding"
+METRIC = "decoded tokens/sec (mean accepted len/step in config.accepted_tokens_per_step), Sequoia tree speculative decoding, 68m->7B Llama (config c2 unless --config says otherwise)"
 
 
 def load_peaks():
