@@ -72,6 +72,8 @@ DECODE_CASES = {
     # draft == target weights: forces deep acceptance paths / multi-row KV gathers
     "spec_same_8x8": ("L40_growmaps/8x8-tree.pt", "spec", "draft", "draft", 256, 26, 80, 5, 17),
     "greedy_same_16chain": ("L40_growmaps/16-chain.pt", "greedy", "draft", "draft", 256, 16, 70, 4, 17),
+    # config-4 tree shape (768 nodes, 18 levels, M=1024): 6 query tiles x 8 KV splits in the attention kernel
+    "spec_l40_768": ("L40_growmaps/L40-CNN-7b-70b-stochastic.pt", "spec", "draft", "target_gqa", 1024, 31, 128, 2, 17),
 }
 
 _MODELS = {"draft": (CFG_DRAFT, DRAFT_SEED), "target": (CFG_TARGET, TARGET_SEED),
