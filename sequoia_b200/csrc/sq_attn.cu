@@ -181,11 +181,11 @@ struct TcSmem {
   static constexpr int OFF_BAR = OFF_X + 2048;          // 3 mbarriers + tmem ptr
   // Split-KV reduction buffers, written REMOTELY by the peer CTAs of the cluster (push model), so they may not alias
   // the Q/K/V tiles: row r of the tile is owned by CTA (r % Z); slot [src split][r / Z] holds that split's partial.
-  static constexpr int O_STRIDE = D + 4;                // floats
+  static constexpr int O_STRIDE = D + 8;                // halfs: partial rows travel as NORMALISED fp16 (O_s / l_s)
   static constexpr int R_ROWS = 128 + 8;                // Z * ceil(128 / Z) <= 136 for Z <= 8
-  static constexpr int OFF_RML = OFF_BAR + 64;          // R_ROWS x float2 (log2-domain max, sum)
-  static constexpr int OFF_R = OFF_RML + R_ROWS * 8;    // R_ROWS x O_STRIDE floats
-  static constexpr int TOTAL = OFF_R + R_ROWS * O_STRIDE * 4;
+  static constexpr int OFF_RML = OFF_BAR + 64;          // [owned row][8 splits] float2 (log2-domain max, sum)
+  static constexpr int OFF_R = OFF_RML + 128 * 8 * 8;   // R_ROWS x O_STRIDE floats   (<= 128 owned rows per CTA)
+  static constexpr int TOTAL = OFF_R + R_ROWS * O_STRIDE * 2;
 };
 
 #define SQ_STAMP(k) do { if (a.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.dbg[split * 16 + (k)] = clock64(); } while (0)
@@ -416,39 +416,45 @@ __global__ void __launch_bounds__(256, 1)
     ptx::tc_fence_after();
     SQ_STAMP(5);
 
-    // stage this split's partial O (unnormalised fp32) row-major in the now dead Q/K/V tiles ...
-    float* sO = reinterpret_cast<float*>(smem);
+    // stage this split's partial O, normalised by this split's row sum and rounded to fp16 (|O_s / l_s| <= max|v|), row-major
+    // in the now dead Q/K/V tiles ...
+    __half* sO = reinterpret_cast<__half*>(smem);
     {
+      const float lrow_sum = sxsum[trow] + sxsum[128 + trow];
+      const float linv = lrow_sum > 0.f ? 1.f / lrow_sum : 0.f;
 #pragma unroll 1
       for (int jj = 0; jj < D / 64; ++jj) {
         const int j = hf * (D / 64) + jj;
         uint32_t r[32];
         ptx::tmem_ld32(tm_O + lane_base + j * 32, r);
 #pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          *reinterpret_cast<uint4*>(sO + trow * SM::O_STRIDE + j * 32 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+        for (int e = 0; e < 32; e += 8) {
+          Pack8 o;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o.h[q] = f2h(__uint_as_float(r[e + q]) * linv);
+          *reinterpret_cast<uint4*>(sO + trow * SM::O_STRIDE + j * 32 + e) = o.u;
+        }
       }
-      if (hf == 0)
-        st_cluster_v2(mapa_u32(sRML_local, owner) + (uint32_t)((split * rpc + lrow) * 8), mx, sxsum[trow] + sxsum[128 + trow]);
+      if (hf == 0) st_cluster_v2(mapa_u32(sRML_local, owner) + (uint32_t)((lrow * 8 + split) * 8), mx, lrow_sum);
     }
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 0) ptx::tmem_dealloc(tmem, 512);
     SQ_STAMP(10);
-    // ... and push every row to the CTA that owns it: one warp moves one row (512 B contiguous remote store)
+    // ... and push every row to the CTA that owns it: D/8 lanes move one row (16 B each, contiguous remote store)
     {
-      constexpr int CPR = D / 4, RPW = 32 / CPR;
+      constexpr int CPR = D / 8, RPW = 32 / CPR;
       const int sub = lane / CPR, cc = lane % CPR;
 #pragma unroll 4
       for (int rr = warp * RPW + sub; rr < TILE_Q; rr += 8 * RPW) {
-        const uint4 val = *reinterpret_cast<const uint4*>(sO + rr * SM::O_STRIDE + cc * 4);
-        const uint32_t dst = mapa_u32(sR_local, (uint32_t)(rr % Z)) + (uint32_t)(((split * rpc + rr / Z) * SM::O_STRIDE + cc * 4) * 4);
+        const uint4 val = *reinterpret_cast<const uint4*>(sO + rr * SM::O_STRIDE + cc * 8);
+        const uint32_t dst = mapa_u32(sR_local, (uint32_t)(rr % Z)) + (uint32_t)(((split * rpc + rr / Z) * SM::O_STRIDE + cc * 8) * 2);
         st_cluster_v4(dst, val.x, val.y, val.z, val.w);
       }
     }
     SQ_STAMP(6);
   } else if (split < nsplit && hf == 0) {
-    st_cluster_v2(mapa_u32(sRML_local, owner) + (uint32_t)((split * rpc + lrow) * 8), -INFINITY, 0.f);
+    st_cluster_v2(mapa_u32(sRML_local, owner) + (uint32_t)((lrow * 8 + split) * 8), -INFINITY, 0.f);
   }
 
   // ---- split-KV reduction: every CTA normalises the rows it owns, from its OWN shared memory -------------------------
@@ -456,44 +462,57 @@ __global__ void __launch_bounds__(256, 1)
   SQ_STAMP(7);
   {
     const float2* sRML = reinterpret_cast<const float2*>(smem + SM::OFF_RML);
-    const float* sR = reinterpret_cast<const float*>(smem + SM::OFF_R);
+    const __half* sR = reinterpret_cast<const __half*>(smem + SM::OFF_R);
     float* wts = reinterpret_cast<float*>(smem + SM::OFF_MASK);       // [rpc][8] normalised split weights (mask is dead)
-    // phase 1: one thread per owned row -> weight of every split: 2^(m_s - m) / sum_s 2^(m_s - m) l_s
+    // phase 1: one thread per owned row -> weight of every split: 2^(m_s - m) / sum_s 2^(m_s - m) l_s.  All 8 (max, sum)
+    // pairs of the row are fetched with four 16-byte loads before any arithmetic (this code is latency-bound).
     if (tid < rpc) {
+      const float4* mlp = reinterpret_cast<const float4*>(sRML + tid * 8);
+      float4 q[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q[i] = mlp[i];
+      float m[8], l[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { m[2 * i] = q[i].x; l[2 * i] = q[i].y; m[2 * i + 1] = q[i].z; l[2 * i + 1] = q[i].w; }
       float mm = -INFINITY;
-      for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, sRML[s * rpc + tid].x);
-      float den = 0.f;
-      for (int s = 0; s < nsplit; ++s) {
-        const float2 ml = sRML[s * rpc + tid];
-        const float f = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - mm);
-        wts[tid * 8 + s] = f;
-        den += f * ml.y;
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) { if (sp >= nsplit) m[sp] = -INFINITY; mm = fmaxf(mm, m[sp]); }
+      float f[8], den = 0.f;
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) {            // partial rows arrive normalised by l_s: weight = 2^(m_s-m) * l_s / den
+        f[sp] = (m[sp] == -INFINITY) ? 0.f : exp2f(m[sp] - mm) * l[sp];
+        den += f[sp];
       }
       const float inv = den > 0.f ? 1.f / den : 0.f;
-      for (int s = 0; s < nsplit; ++s) wts[tid * 8 + s] *= inv;
+      float4* wp = reinterpret_cast<float4*>(wts + tid * 8);
+      wp[0] = make_float4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
+      wp[1] = make_float4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
     }
     __syncthreads();
     SQ_STAMP(9);
-    // phase 2: flat, dependency-free weighted sum over (row, 4-column chunk)
-    constexpr int CPR = D / 4;
-#pragma unroll 2
+    // phase 2: flat weighted sum over (row, 8-column chunk); weights and all partial chunks are loaded up front
+    constexpr int CPR = D / 8;
+#pragma unroll 1
     for (int i = tid; i < rpc * CPR; i += 256) {
       const int lr = i / CPR, cc = i % CPR;
       const int rr = lr * Z + split;             // tile row owned by this CTA
       if (rr >= TILE_Q || q0 + rr >= a.n) continue;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < nsplit; ++s) {
-        const float w = wts[lr * 8 + s];
-        if (w == 0.f) continue;                  // masked / empty split: its O slot was never written
-        const float4 o = (a.debug_flags & 4) ? make_float4(1.f, 2.f, 3.f, 4.f)
-                                             : *reinterpret_cast<const float4*>(sR + (s * rpc + lr) * SM::O_STRIDE + cc * 4);
-        acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
-      }
-      const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-      if (!(a.debug_flags & 2)) *reinterpret_cast<uint2*>(a.out + (int64_t)(q0 + rr) * (a.H * D) + h * D + cc * 4) = pk;
+      const float4 w0 = *reinterpret_cast<const float4*>(wts + lr * 8), w1 = *reinterpret_cast<const float4*>(wts + lr * 8 + 4);
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      Pack8 o[8];
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp)             // a zero weight marks a masked / inactive split whose slot was never written
+        o[sp].u = (sp < Z && w[sp] != 0.f) ? *reinterpret_cast<const uint4*>(sR + (sp * rpc + lr) * SM::O_STRIDE + cc * 8)
+                                           : make_uint4(0, 0, 0, 0);
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += w[sp] * h2f(o[sp].h[e]);
+      Pack8 res;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) res.h[e] = f2h(acc[e]);
+      *reinterpret_cast<uint4*>(a.out + (int64_t)(q0 + rr) * (a.H * D) + h * D + cc * 8) = res.u;
     }
   }
   SQ_STAMP(8);
