@@ -102,6 +102,7 @@ def run_b200(args):
     dev = f"cuda:{local}"
     tp_group = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SQ_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
         tp_group = dist.group.WORLD
     dname, tname, gm_path, greedy, T, top_p, M, prefix, max_len = CONFIGS[args.config]

@@ -58,19 +58,30 @@ __global__ void __launch_bounds__(256) tp_allreduce_add_rmsnorm_kernel(TpArgs t,
   const int nvec = hidden / 8;
   Pack8 v[MAXV];
   float ss = 0.f;
+  // Peer loads cross NVLink (~2 us each): issue ALL of them (every chunk of this thread x every rank) before the first
+  // use, instead of paying the latency once per rank and chunk.
+  Pack8 part[MAXV][8];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      part[i][s].u = make_uint4(0, 0, 0, 0);
+      if (c < nvec && s < t.N) {
+        const uint4* src = reinterpret_cast<const uint4*>(t.proj[s] + (int64_t)r * hidden) + c;
+        part[i][s].u = (s == t.rank) ? *src : ld_relaxed_sys_v4(src);
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = tid + i * 256;
     if (c < nvec) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int s = 0; s < t.N; ++s) {                         // fixed order => every rank computes the same bits
-        Pack8 p;
-        const __half* src = t.proj[s] + (int64_t)r * hidden;
-        if (s == t.rank) p.u = reinterpret_cast<const uint4*>(src)[c];
-        else p.u = ld_relaxed_sys_v4(reinterpret_cast<const uint4*>(src) + c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += h2f(p.h[j]);
-      }
+      for (int s = 0; s < 8; ++s)                             // fixed rank order => every rank computes the same bits
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += h2f(part[i][s].h[j]);   // (+0 for s >= N)
       Pack8 a;
       a.u = reinterpret_cast<const uint4*>(resid + (int64_t)r * hidden)[c];
 #pragma unroll
