@@ -102,8 +102,19 @@ def run_b200(args):
     dev = f"cuda:{local}"
     tp_group = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SQ_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        # NCCL prints its version banner on stdout when the first communicator is created; the contract is ONE JSON line,
+        # so create the communicator with fd 1 pointed at /dev/null
+        sys.stdout.flush()
+        saved_fd, null_fd = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null_fd, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(dev))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(null_fd)
+            os.close(saved_fd)
         tp_group = dist.group.WORLD
     dname, tname, gm_path, greedy, T, top_p, M, prefix, max_len = CONFIGS[args.config]
     grow_map = torch.load(os.path.join(ROOT, gm_path))
