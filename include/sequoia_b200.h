@@ -81,8 +81,9 @@ int sq_kv_gather(sq_half* k_cache, sq_half* v_cache, int L, int Hkv, int M, int 
 
 /* ---- tree-masked attention (Llama_modules.py:127-134 draft SDPA, :220-248 target explicit attention) ---- */
 
-/* Opaque plan: TMA descriptors + split-KV workspace for one (q buffer, cache) pair.  Host call, not capturable;
- * create once per engine / width and reuse inside graphs. */
+/* Opaque plan: TMA descriptors (+ a small debug workspace) for one (q buffer, cache) pair.  Host call, not capturable;
+ * create once per engine and reuse inside graphs.  (Split-KV partials are reduced through distributed shared memory
+ * inside the kernel; no global workspace.) */
 typedef struct sq_attn_plan sq_attn_plan;
 /* q: (n_max rows, ld) fp16 with head h at columns [h*D,(h+1)*D); k_cache/v_cache: (L,1,Hkv,M,D);
  * out: (n_max, H*D) fp16.  workspace: device buffer of sq_attn_workspace_bytes(...) bytes. */

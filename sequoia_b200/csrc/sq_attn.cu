@@ -1,7 +1,8 @@
 // Tree-masked attention for the draft (Engine/Llama_modules.py:127-134) and target / verify
 // (Engine/Llama_modules.py:220-248) forwards.
 //
-// Product kernel (impl 0): one CTA per (head, 128-row query tile, 128-key KV split).
+// Product kernel (impl 0): grid (heads, 128-row query tiles, 128-key KV splits) launched as thread-block clusters
+// (1,1,Z) -- the Z CTAs of a cluster are the KV splits of one (head, q tile); 256 threads per CTA.
 //   * Q, K and V tiles are staged in shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_128B) straight from the
 //     fused qkv activation and the static (L,1,Hkv,M,D) caches;
 //   * S = Q K^T and O = P V run on the 5th-gen tensor cores (tcgen05.mma, kind::f16, M=128) with the accumulators
@@ -9,9 +10,12 @@
 //   * the tree-causal mask is NOT a dense fp16 (M,M) tensor: the growmap's ancestor matrix is packed 1 bit / pair,
 //     the query tile's bit rows are staged in shared memory and combined with the device-resident prefix length;
 //     a dense additive mask (the reference API) is supported through a shared-memory tile as well;
-//   * split-KV partials (fp32 O, running max, sum) go to a workspace and a small combine kernel normalises them, so
-//     32 heads x 3 splits (config 2) or 8 heads x 6 q-tiles x 8 splits (config 4 / TP-8) fill the 148 SMs.
-// Roofline: HBM-bound for configs 2/3 (bytes = 2*D*2*(Hkv*kv + H*q) per layer), tensor-pipe-bound for config 4.
+//   * split-KV: every CTA pushes its partial rows (normalised fp16 O_s / l_s, log2-domain max, sum) into the shared
+//     memory of the row's owner CTA (st.shared::cluster), one cluster barrier, owners combine and store fp16 -- no
+//     global workspace, no second kernel.  32 heads x 3 splits (config 2) or 8 heads x 6 q-tiles x 8 splits
+//     (config 4 / TP-8) spread over the 148 SMs.
+// Roofline: HBM-bound for configs 2/3 (bytes = 2*D*2*(Hkv*kv + H*q) per layer), tensor-pipe-bound for config 4; at
+// these sizes the kernel is latency-bound in practice (profiles/r01_attn_ncu.md).
 //
 // impl 1 is a plain SIMT kernel used by the tests as an on-device cross-check of the tensor-core path.
 #include <cooperative_groups.h>
@@ -29,12 +33,9 @@ struct sq_attn_plan {
   const __half* k_cache;
   const __half* v_cache;
   __half* out;
-  float* ws_o;    // [splits][H][n_pad][D]
-  float* ws_ml;   // [splits][H][n_pad][2]
-  int n_pad, splits_max;
+  int splits_max;
   int debug_flags;
   int* err_flag;  // device word set by a watchdog timeout
-  int* counters;  // [H][n_pad/128] split arrival counters
   long long* dbg; // phase timestamps (SQ_ATTN_TIMING=1)
   CUtensorMap tm_q, tm_k, tm_v;
 };
@@ -51,9 +52,7 @@ struct AttnArgs {
   const __half* k_layer;   // (Hkv, M, D) of this layer
   const __half* v_layer;
   __half* out;
-  float* ws_o;
-  float* ws_ml;
-  int n, n_pad, H, Hkv, M;
+  int n, H, Hkv, M;
   int layer;
   const int32_t* state;
   int n0, kv_end, prefix_len_host;
@@ -64,7 +63,6 @@ struct AttnArgs {
   float scale;
   int debug_flags;
   int* err_flag;
-  int* counters;           // (unused by the cluster kernel)
   long long* dbg;          // optional phase timestamps (SQ_ATTN_TIMING=1): [split][16] clock64 values of CTA (0,0,split)
 };
 
@@ -552,9 +550,8 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
 }
 
 extern "C" int64_t sq_attn_workspace_bytes(int n_max, int H, int D, int M) {
-  const int64_t n_pad = ((n_max + TILE_Q - 1) / TILE_Q) * TILE_Q;
-  const int64_t splits = (M + TILE_KV - 1) / TILE_KV;
-  return splits * H * n_pad * (D + 2) * 4 + 256 + (int64_t)H * (n_pad / TILE_Q) * 4 + 8 * 16 * 8 + 64;
+  (void)n_max; (void)H; (void)D; (void)M;
+  return 256 + 8 * 16 * 8;   // watchdog word + optional phase timestamps (the split-KV partials live in shared memory)
 }
 
 extern "C" int sq_attn_plan_create(sq_attn_plan** plan, const sq_half* q, int ld, int n_max, int H, int Hkv, int D,
@@ -569,21 +566,15 @@ extern "C" int sq_attn_plan_create(sq_attn_plan** plan, const sq_half* q, int ld
   sq_attn_plan* p = new sq_attn_plan();
   p->q = (const __half*)q; p->ld = ld; p->n_max = n_max; p->H = H; p->Hkv = Hkv; p->D = D; p->L = L; p->M = M;
   p->k_cache = (const __half*)k_cache; p->v_cache = (const __half*)v_cache; p->out = (__half*)out;
-  p->n_pad = ((n_max + TILE_Q - 1) / TILE_Q) * TILE_Q;
   p->splits_max = (M + TILE_KV - 1) / TILE_KV;
-  p->ws_o = (float*)workspace;
-  p->ws_ml = p->ws_o + (int64_t)p->splits_max * H * p->n_pad * D;
-  p->err_flag = (int*)(p->ws_ml + (int64_t)p->splits_max * H * p->n_pad * 2);
-  p->counters = p->err_flag + 64;
+  p->err_flag = (int*)workspace;
   {
-    uintptr_t d = (uintptr_t)(p->counters + (int64_t)H * (p->n_pad / TILE_Q));
-    d = (d + 15) & ~(uintptr_t)15;
     const char* tenv = getenv("SQ_ATTN_TIMING");
-    p->dbg = (tenv && atoi(tenv)) ? (long long*)d : nullptr;
+    p->dbg = (tenv && atoi(tenv)) ? (long long*)((char*)workspace + 256) : nullptr;
   }
   const char* dbg = getenv("SQ_ATTN_DEBUG");
   p->debug_flags = dbg ? atoi(dbg) : 0;
-  cudaMemset(p->err_flag, 0, 256 + (size_t)H * (p->n_pad / TILE_Q) * 4);
+  cudaMemset(workspace, 0, 256 + 8 * 16 * 8);
   {
     cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)n_max};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
@@ -668,13 +659,13 @@ extern "C" int sq_tree_attn(sq_attn_plan* plan, int layer, int n, const int32_t*
   a.q = plan->q; a.ld = plan->ld;
   a.k_layer = plan->k_cache + (int64_t)layer * plan->Hkv * plan->M * plan->D;
   a.v_layer = plan->v_cache + (int64_t)layer * plan->Hkv * plan->M * plan->D;
-  a.out = plan->out; a.ws_o = plan->ws_o; a.ws_ml = plan->ws_ml;
-  a.n = n; a.n_pad = plan->n_pad; a.H = plan->H; a.Hkv = plan->Hkv; a.M = plan->M; a.layer = layer;
+  a.out = plan->out;
+  a.n = n; a.H = plan->H; a.Hkv = plan->Hkv; a.M = plan->M; a.layer = layer;
   a.state = state; a.n0 = n0; a.kv_end = kv_end; a.prefix_len_host = prefix_len_host;
   a.dense_mask = (const __half*)dense_mask; a.mask_ld = mask_ld;
   a.tree_bits = tree_bits; a.tree_words = tree_bits ? tree_words : 0; a.tree_size = tree_bits ? tree_size : 0;
   a.scale = 1.0f / sqrtf((float)plan->D);
-  a.debug_flags = plan->debug_flags; a.err_flag = plan->err_flag; a.counters = plan->counters; a.dbg = plan->dbg;
+  a.debug_flags = plan->debug_flags; a.err_flag = plan->err_flag; a.dbg = plan->dbg;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->D == 64) return launch_attn<64>(plan, a, impl, st);
   return launch_attn<128>(plan, a, impl, st);
