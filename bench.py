@@ -32,6 +32,8 @@ CONFIGS = {
     "c1": ("llama-68m", "llama-160m", "L40_growmaps/2-chain.pt", True, 0.6, 1.0, 256, 128, 256),
     "c2": ("llama-68m", "llama-2-7b", "A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt", False, 0.6, 1.0, 384,
            128, 256),
+    # c2 with the growmap tree_search.py derives from this GPU's measured draft/verify times (B200_growmaps/)
+    "c2b": ("llama-68m", "llama-2-7b", "B200_growmaps/68m_7b-demo_acceptance.pt", False, 0.6, 1.0, 384, 128, 256),
     "c3": ("llama-68m", "llama-2-13b", "L40_growmaps/8x8-tree.pt", False, 0.6, 1.0, 384, 128, 256),
     "c4": ("llama-2-7b", "llama-2-70b", "L40_growmaps/L40-CNN-7b-70b-stochastic.pt", False, 0.6, 1.0, 1024, 128, 256),
 }

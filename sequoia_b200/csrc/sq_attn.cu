@@ -272,12 +272,35 @@ __global__ void __launch_bounds__(256, 1)
     uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + SM::OFF_MASK);
     __half* smask = reinterpret_cast<__half*>(smem + SM::OFF_MASK);
     if (DENSE) {
-#pragma unroll 4
-      for (int i = tid; i < TILE_Q * TILE_KV; i += 256) {
-        const int rr = i >> 7, cc = i & 127;
-        __half v = __float2half(0.f);
-        if (q0 + rr < a.n && kv0 + cc < kv_len) v = a.dense_mask[(int64_t)(q0 + rr) * a.mask_ld + kv0 + cc];
-        smask[rr * 132 + cc] = v;
+      // additive fp16 mask tile -> smem.  Rows of an aligned mask go as 16 B vectors (8 loads per thread, all in
+      // flight); a mask view with odd leading dimension / base falls back to coalesced 2 B loads.
+      const bool vec = ((reinterpret_cast<uintptr_t>(a.dense_mask) | (uintptr_t)(a.mask_ld * 2)) & 15u) == 0;
+      if (vec) {
+#pragma unroll
+        for (int i = tid; i < TILE_Q * (TILE_KV / 8); i += 256) {
+          const int rr = i >> 4, cc = (i & 15) * 8;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (q0 + rr < a.n && kv0 + cc + 8 <= kv_len) {
+            v = *reinterpret_cast<const uint4*>(a.dense_mask + (int64_t)(q0 + rr) * a.mask_ld + kv0 + cc);
+          } else if (q0 + rr < a.n && kv0 + cc < kv_len) {      // ragged last vector of the row: stay inside kv_len
+            __half t[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              t[e] = (kv0 + cc + e < kv_len) ? a.dense_mask[(int64_t)(q0 + rr) * a.mask_ld + kv0 + cc + e] : __float2half(0.f);
+            v = *reinterpret_cast<const uint4*>(t);
+          }
+          uint2* dst = reinterpret_cast<uint2*>(smask + rr * 132 + cc);   // row stride 264 B: 8 B aligned
+          dst[0] = make_uint2(v.x, v.y);
+          dst[1] = make_uint2(v.z, v.w);
+        }
+      } else {
+#pragma unroll 16
+        for (int i = tid; i < TILE_Q * TILE_KV; i += 256) {
+          const int rr = i >> 7, cc = i & 127;
+          __half v = __float2half(0.f);
+          if (q0 + rr < a.n && kv0 + cc < kv_len) v = a.dense_mask[(int64_t)(q0 + rr) * a.mask_ld + kv0 + cc];
+          smask[rr * 132 + cc] = v;
+        }
       }
     } else if (a.tree_words > 0 && hf == 0) {    // one thread per row copies that row's ancestor words
       const int node = slot - (P - 1);
@@ -627,8 +650,12 @@ static int launch_attn(sq_attn_plan* p, AttnArgs& a, int impl, cudaStream_t st) 
     attr_set[a.dense_mask ? 1 : 0] = true;
   }
   const int q_tiles = (a.n + TILE_Q - 1) / TILE_Q;
+  // KV splits per cluster: every split the cache could need when the length lives in the device state (graph-static
+  // launch); exactly the splits this call touches when the host knows kv_end (engine API with an explicit mask)
+  int Z = p->splits_max;
+  if (a.state == nullptr) Z = std::max(1, std::min(Z, (a.kv_end + TILE_KV - 1) / TILE_KV));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(a.H, q_tiles, p->splits_max);
+  cfg.gridDim = dim3(a.H, q_tiles, Z);
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -636,7 +663,7 @@ static int launch_attn(sq_attn_plan* p, AttnArgs& a, int impl, cudaStream_t st) 
   attr[0].id = cudaLaunchAttributeClusterDimension;     // the KV splits of one (head, q tile) form a cluster
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = p->splits_max;
+  attr[0].val.clusterDim.z = Z;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p->tm_q, p->tm_k, p->tm_v, a);
