@@ -129,6 +129,16 @@ int sq_sample_level(const sq_half* logits, int64_t ld_logits, const sq_half* ran
                     int k_max, int V, float T, int mode, int64_t* positions, int64_t* tokens, const int32_t* state,
                     void* stream);
 
+/* One tree level of SpecInfer-style drafting (Tree/SpecInferTree.py:100-105): children drawn i.i.d. WITH replacement
+ * from q = softmax(fp16(logits_row / T)) (fp16).  Exact integer inverse-CDF: w_v = q_v * 2^24 (exact), draw c is the
+ * first v whose inclusive prefix sum exceeds (words[wbase + c] * sum_v w_v) >> 32, words = uniform integers in
+ * [0, 2^32) stored as int64 (the caller's RNG; the reference uses torch.multinomial's).  wbase = child_first[j]
+ * (node id of the first child) or j*k_max when child_first is NULL; n_branch[j] (or k_max) draws per parent, written
+ * to positions[j*k_max + c] (may be NULL) and tokens[base + child_first[j] + c] (may be NULL). */
+int sq_sample_replace(const sq_half* logits, int64_t ld_logits, const int64_t* words, const int32_t* parent_rows,
+                      const int32_t* child_first, const int32_t* n_branch, int n_parents, int k_max, int V, float T,
+                      int64_t* positions, int64_t* tokens, const int32_t* state, void* stream);
+
 /* get_residual (utils.py:5-8): out = relu(p-q) / sum(relu(p-q)), fp16 roundings as torch. */
 int sq_residual(const sq_half* p, const sq_half* q, sq_half* out, int V, void* stream);
 
@@ -148,11 +158,15 @@ int sq_argmax_rows(const sq_half* logits, int64_t ld, int n, int V, int64_t* out
  * Then (SpecTree.py:224, 261-271): compact tokens / position_ids, write the bonus token, re-lay tree positions,
  * and publish state[] (P, accept_len, terminal, n_new, P_old, bonus, nan, skipped) and accept_idx[0..n_new).
  * target_logits: (S, V) raw logits rows (row k = node k).  draft_logits: (>=S, V) rows, READ ONLY (the masking
- * of rejected tokens is kept on chip; the reference's in-place edit is dead state).  */
+ * of rejected tokens is kept on chip; the reference's in-place edit is dead state).
+ * policy: 0 = SpecTree.  SQ_ACCEPT_GE: accept on >= ; SQ_ACCEPT_KEEP_Q: q is not edited after a rejection — both set
+ * = the SpecInfer walk (Tree/SpecInferTree.py:143-162).  */
+#define SQ_ACCEPT_GE 1
+#define SQ_ACCEPT_KEEP_Q 2
 int sq_accept_stochastic(const sq_half* target_logits, int64_t ld_t, const sq_half* draft_logits, int64_t ld_d,
                          const sq_half* r, const sq_half* noise, const int32_t* succ_off, const int32_t* succ,
                          const int32_t* depth, int S, int V, float T, int64_t* tokens, int64_t* position_ids,
-                         int32_t* accept_idx, int32_t* state, int max_target_seq, void* stream);
+                         int32_t* accept_idx, int32_t* state, int max_target_seq, int policy, void* stream);
 /* Greedy walk (GreedyTree.py): target_token (S) int64 from sq_argmax_rows; accept the first child whose token
  * equals target_token[cur]; bonus = target_token[last accepted]. Same outputs as above. */
 int sq_accept_greedy(const int64_t* target_token, const int32_t* succ_off, const int32_t* succ,

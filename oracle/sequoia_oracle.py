@@ -564,6 +564,9 @@ class GreedyTreeOracle(SpecTreeOracle):
         g = self.ground_truth_len
         self.draft_logits[start_pos - g + 1:end_pos - g + 1] = out[0][-total_branch:]
 
+    def _target_tokens(self) -> torch.Tensor:                                       # GreedyTree.py:186
+        return self.target_logits.argmax(dim=-1)
+
     def accept_step(self, parent_id: int) -> int:                                   # GreedyTree.py:132-146
         g = self.ground_truth_len
         logits_id = parent_id - (g - 1)
@@ -583,7 +586,7 @@ class GreedyTreeOracle(SpecTreeOracle):
                                     self.position_ids[start_pos:end_pos].unsqueeze(0), attn_mask)
         self.target_logits = out[0][g - 1:] if self.target_kv_len == 0 else out[0][-new_node_num:]
         self.raw_target_logits = self.target_logits
-        self.target_token = self.target_logits.argmax(dim=-1)
+        self.target_token = self._target_tokens()
         tree_tokens = self.tokens[g:g + self.S - 1].clone()
         accept_list = list(range(g))
         terminal = False
@@ -611,6 +614,105 @@ class GreedyTreeOracle(SpecTreeOracle):
             valid = self.tokens[:a]
         self.last_trace = IterTrace(g, tree_tokens, list(accept_list), bonus, terminal, valid.clone())
         return valid, a, a, terminal
+
+
+class GreedySTreeOracle(GreedyTreeOracle):
+    """Tree/GreedySTree.py restated: GreedyTree drafting (top-k children) verified against a target token SAMPLED
+    from softmax(top_p(target_logits) / T) instead of the argmax (GreedySTree.py:188-190).
+
+    target_words: optional (n_iter, S, V) fp16 uniforms; when given, row k's token is the k=1 exponential race
+    argmax(log(u) / p) (`sampling_without_replacement`, the same draw torch.multinomial(1) makes from its own
+    noise) so that a GPU run fed the same uniforms is comparable; when None the oracle calls torch.multinomial
+    exactly like the reference."""
+
+    def __init__(self, draft, target, prefix, grow_map, temperature=0.6, top_p=1.0, max_length=256,
+                 max_target_seq=None, vocab_size=32000, target_uniforms: Optional[torch.Tensor] = None):
+        super().__init__(draft, target, prefix, grow_map, max_length=max_length, max_target_seq=max_target_seq,
+                         vocab_size=vocab_size)
+        self.T, self.top_p = temperature, top_p
+        self.target_uniforms = target_uniforms
+
+    def _target_tokens(self) -> torch.Tensor:                                       # GreedySTree.py:188-190
+        lg = get_sampling_logits(self.target_logits, self.top_p, self.T, replicate=False)
+        if self.target_uniforms is not None:
+            return sampling_without_replacement(lg, self.target_uniforms[self.iter], 1, self.T)
+        self.target_logits = softmax(lg / self.T, dim=-1)
+        return self.target_logits.multinomial(num_samples=1).flatten()
+
+
+def multinomial_words(q: torch.Tensor, words: torch.Tensor) -> torch.Tensor:
+    """Sampling WITH replacement from fp16 probability rows by exact integer inverse-CDF.
+
+    Every fp16 value in [0, 1] is an integer multiple of 2^-24, so w = q * 2^24 is an exact integer weight, prefix sums
+    are exact and order-independent, and draw j of row i is the first index whose inclusive prefix sum exceeds
+    (words[i, j] * total_i) >> 32 with words uniform in [0, 2^32).  The CUDA kernel (sq_sample_replace) does the same
+    arithmetic, so given identical q rows the two agree bit for bit.  q: (rows, V) fp16; words: (rows, k) int64."""
+    w = (q.double() * 16777216.0).round().long()
+    cdf = w.cumsum(-1)
+    total = cdf[:, -1:]
+    t = (words.long() * total) >> 32
+    return torch.searchsorted(cdf, t, right=True).clamp_(max=q.shape[-1] - 1)
+
+
+class SpecInferTreeOracle(SpecTreeOracle):
+    """Tree/SpecInferTree.py restated (the SpecInfer baseline policy behind the same tree machinery): children are
+    drawn i.i.d. WITH replacement from softmax(draft/T) (:100-105), the walk accepts on `>=` and never masks a
+    rejected token out of q (:143-162); everything else is SpecTree.
+
+    sample_words: optional (n_iter, S) int64 words in [0, 2^32): node k's token is drawn with words[iter, k] through
+    `multinomial_words`; forced_tokens: optional callable(iter) -> (S-1,) tree tokens to install instead of sampling
+    (lock-step tests feed the GPU's tree).  With neither, torch.multinomial is called exactly like the reference."""
+
+    def __init__(self, *a, sample_words: Optional[torch.Tensor] = None, forced_tokens=None, **kw):
+        super().__init__(*a, **kw)
+        self.sample_words = sample_words
+        self.forced_tokens = forced_tokens
+
+    def collective_grow_static(self, idx_list, n_branch_list, grow_step):            # SpecInferTree.py:88-134
+        total_branch = sum(n_branch_list)
+        k = max(n_branch_list)
+        q = softmax(self.draft_logits[idx_list] / self.T, dim=-1)
+        g = self.ground_truth_len
+        first_child = self.num_nodes - g + 1                                         # node id of this level's first child
+        if self.forced_tokens is not None:
+            new = self.forced_tokens(self.iter)[first_child - 1:first_child - 1 + total_branch]
+            self.tokens[self.num_nodes:self.num_nodes + total_branch] = new
+        elif self.sample_words is not None:
+            words = torch.zeros((len(n_branch_list), k), dtype=torch.long)
+            c = first_child
+            for j, nb in enumerate(n_branch_list):
+                words[j, :nb] = self.sample_words[self.iter, c:c + nb]
+                c += nb
+            new_tokens_set = multinomial_words(q, words).flatten()
+            self.tokens[self.num_nodes:self.num_nodes + total_branch] = new_tokens_set[self.gather_idx[grow_step]]
+        else:
+            new_tokens_set = q.multinomial(num_samples=k, replacement=True).flatten()
+            self.tokens[self.num_nodes:self.num_nodes + total_branch] = new_tokens_set[self.gather_idx[grow_step]]
+        self.num_nodes += total_branch
+        start_pos, end_pos = self.num_nodes - total_branch, self.num_nodes
+        attn_mask = self.attn_mask[start_pos:end_pos][None, None, :, :]
+        out = self.draft.graph_inference(self.tokens[self.draft_kv_len:self.num_nodes].unsqueeze(0),
+                                         self.storage_ids[self.draft_kv_len:self.num_nodes],
+                                         self.position_ids[start_pos:end_pos].unsqueeze(0), attn_mask)
+        self.draft_kv_len = self.num_nodes
+        self.draft_logits[start_pos - g + 1:end_pos - g + 1] = out[0][-total_branch:]
+
+    def accept_step(self, parent_id: int):                                           # SpecInferTree.py:143-162
+        g = self.ground_truth_len
+        logits_id = parent_id - (g - 1)
+        p = self.target_logits[logits_id]
+        draft_logits = self.draft_logits[logits_id]
+        children = self.Successors[logits_id]
+        if len(children) == 0:
+            return -1, p
+        for pos in children:
+            token = self.tokens[pos + (g - 1)]
+            q = softmax(draft_logits / self.T, dim=-1)
+            r = self.r[pos + (g - 1)]
+            if p[token] >= r * q[token]:
+                return pos + (g - 1), None
+            p = get_residual(p, q)
+        return -1, p
 
 
 # --------------------------------------------------------------------------------------

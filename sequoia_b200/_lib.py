@@ -36,9 +36,10 @@ _SIGNATURES = {
     "sq_tree_attn": (i32, [vp, i32, i32, vp, i32, i32, i32, vp, i64, vp, i32, i32, i32, vp]),
     "sq_softmax_T": (i32, [vp, i64, vp, i64, i32, i32, f32, vp]),
     "sq_sample_level": (i32, [vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp]),
+    "sq_sample_replace": (i32, [vp, i64, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp]),
     "sq_residual": (i32, [vp, vp, vp, i32, vp]),
     "sq_argmax_rows": (i32, [vp, i64, i32, i32, vp, vp]),
-    "sq_accept_stochastic": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, i32, vp]),
+    "sq_accept_stochastic": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, i32, i32, vp]),
     "sq_accept_greedy": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]),
     "sq_gemm_plan_create": (i32, [C.POINTER(vp), vp, i32, i32, vp, i32, i32, vp, i32, vp]),
     "sq_gemm_plan_destroy": (i32, [vp]),

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(ANT) accept_stochastic_kernel(
     const __half* __restrict__ r, const __half* __restrict__ noise, const int32_t* __restrict__ succ_off,
     const int32_t* __restrict__ succ, const int32_t* __restrict__ depth, int S, int V, float inv_T,
     int64_t* __restrict__ tokens, int64_t* __restrict__ position_ids, int32_t* __restrict__ accept_idx,
-    int32_t* __restrict__ state, int max_target_seq) {
+    int32_t* __restrict__ state, int max_target_seq, int policy) {
   __shared__ float red[ANW];
   __shared__ uint32_t redu[ANW];
   __shared__ int32_t sh_acc[1024];
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(ANT) accept_stochastic_kernel(
         const float etok = __expf(h2f(dtok) - mxd);
         const float qtok = h2f(f2h(__fdividef(etok, sumd)));
         const float thr = rnd16(h2f(r[slot]) * qtok);        // r * q[token] in fp16
-        const int acc = (h2f(ptok) > thr) ? 1 : 0;           // strict >   (:152)
-        sh_flag = acc | ((h2f(dtok) >= mxd) ? 2 : 0);        // bit 1: the rejected token holds the running max
+        const int acc = ((policy & SQ_ACCEPT_GE) ? (h2f(ptok) >= thr) : (h2f(ptok) > thr)) ? 1 : 0;   // strict > (:152)
+        sh_flag = acc | ((!(policy & SQ_ACCEPT_KEEP_Q) && h2f(dtok) >= mxd) ? 2 : 0);   // bit 1: rejected token holds the max
         sh_etok = etok;
       }
       __syncthreads();
@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(ANT) accept_stochastic_kernel(
       for (int i = 0; i < ACH; ++i)
 #pragma unroll
         for (int e = 0; e < 8; ++e) p[i].h[e] = f2h(h2f(p[i].h[e]) / tot);
+      if (policy & SQ_ACCEPT_KEEP_Q) continue;               // SpecInfer policy: q is never edited
       // draft_logits[token] = fp16 min   (:156)  ->  scaled value -inf, exp 0
       if (owner) {
         const int ti = tc / ANT;
@@ -236,16 +237,17 @@ extern "C" int sq_accept_stochastic(const sq_half* target_logits, int64_t ld_t, 
                                     int64_t ld_d, const sq_half* r, const sq_half* noise, const int32_t* succ_off,
                                     const int32_t* succ, const int32_t* depth, int S, int V, float T, int64_t* tokens,
                                     int64_t* position_ids, int32_t* accept_idx, int32_t* state, int max_target_seq,
-                                    void* stream) {
+                                    int policy, void* stream) {
   SQ_CHECK_ARG(V % 8 == 0 && V > 0 && V <= ANT * ACH * 8, "sq_accept_stochastic: V=%d unsupported", V);
   SQ_CHECK_ARG(S >= 1 && S <= 1024, "sq_accept_stochastic: S=%d unsupported", S);
+  SQ_CHECK_ARG((policy & ~3) == 0, "sq_accept_stochastic: unknown policy bits %d", policy);
   static const int impl = [] { const char* e = getenv("SQ_ACCEPT_IMPL"); return e ? atoi(e) : 1; }();
   if (impl == 1)   // product path: 8-CTA cluster kernel (sq_accept_cluster.cu); impl 0 = single-CTA cross-check
     return sq::launch_accept_cluster(target_logits, ld_t, draft_logits, ld_d, r, noise, succ_off, succ, depth, S, V, T,
-                                     tokens, position_ids, accept_idx, state, max_target_seq, stream);
+                                     tokens, position_ids, accept_idx, state, max_target_seq, policy, stream);
   accept_stochastic_kernel<<<1, ANT, 0, (cudaStream_t)stream>>>(
       (const __half*)target_logits, ld_t, (const __half*)draft_logits, ld_d, (const __half*)r, (const __half*)noise,
-      succ_off, succ, depth, S, V, 1.0f / T, tokens, position_ids, accept_idx, state, max_target_seq);
+      succ_off, succ, depth, S, V, 1.0f / T, tokens, position_ids, accept_idx, state, max_target_seq, policy);
   SQ_CHECK_LAUNCH("sq_accept_stochastic");
   return SQ_OK;
 }

@@ -73,7 +73,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CNT) accept_stochas
     const __half* __restrict__ r, const __half* __restrict__ noise, const int32_t* __restrict__ succ_off,
     const int32_t* __restrict__ succ, const int32_t* __restrict__ depth, int S, int V, float inv_T,
     int64_t* __restrict__ tokens, int64_t* __restrict__ position_ids, int32_t* __restrict__ accept_idx,
-    int32_t* __restrict__ state, int max_target_seq) {
+    int32_t* __restrict__ state, int max_target_seq, int policy) {
   __shared__ Xch xch;
   __shared__ float red[CNW];
   __shared__ int32_t sh_acc[1024];
@@ -146,9 +146,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CNT) accept_stochas
         if (owner && e == te) {
           const float etok = __expf(h2f(xd.h[e]) - mxd);
           const float thr = rnd16(h2f(r[slot]) * q);         // r * q[token] in fp16
-          const int acc = (h2f(p.h[e]) > thr) ? 1 : 0;       // strict >   (SpecTree.py:152)
+          const float pv = h2f(p.h[e]);
+          // strict > (SpecTree.py:152); the SpecInfer policy accepts on >= (SpecInferTree.py:158)
+          const int acc = ((policy & SQ_ACCEPT_GE) ? (pv >= thr) : (pv > thr)) ? 1 : 0;
           sh_own[0] = etok;
-          sh_own[1] = (float)(acc | ((h2f(xd.h[e]) >= mxd) ? 2 : 0));
+          sh_own[1] = (float)(acc | ((!(policy & SQ_ACCEPT_KEEP_Q) && h2f(xd.h[e]) >= mxd) ? 2 : 0));
         }
       }
       s = block_sum<CNW>(s, red);                            // (contains the barriers that publish sh_own)
@@ -161,8 +163,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CNT) accept_stochas
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         p.h[e] = f2h(h2f(dtmp.h[e]) / tot);                  // get_residual (utils.py:5-8)
-        if (owner && e == te) xd.h[e] = __ushort_as_half((unsigned short)0xFC00u);   // draft_logits[token] = min
+        if (owner && e == te && !(policy & SQ_ACCEPT_KEEP_Q))
+          xd.h[e] = __ushort_as_half((unsigned short)0xFC00u);   // draft_logits[token] = min (SpecTree.py:156)
       }
+      if (policy & SQ_ACCEPT_KEEP_Q) continue;               // SpecInfer: q stays softmax(draft/T) for every child
       if (flag & 2u) {                                       // rare: the masked token held the max -> new statistics
         float m = -INFINITY;
 #pragma unroll
@@ -229,11 +233,11 @@ using namespace sq;
 int sq::launch_accept_cluster(const sq_half* target_logits, int64_t ld_t, const sq_half* draft_logits, int64_t ld_d,
                               const sq_half* r, const sq_half* noise, const int32_t* succ_off, const int32_t* succ,
                               const int32_t* depth, int S, int V, float T, int64_t* tokens, int64_t* position_ids,
-                              int32_t* accept_idx, int32_t* state, int max_target_seq, void* stream) {
+                              int32_t* accept_idx, int32_t* state, int max_target_seq, int policy, void* stream) {
   SQ_CHECK_ARG(V % 8 == 0 && V > 0 && V <= CL * CNT * 8, "sq_accept_stochastic: V=%d unsupported", V);
   accept_stochastic_cluster_kernel<<<CL, CNT, 0, (cudaStream_t)stream>>>(
       (const __half*)target_logits, ld_t, (const __half*)draft_logits, ld_d, (const __half*)r, (const __half*)noise,
-      succ_off, succ, depth, S, V, 1.0f / T, tokens, position_ids, accept_idx, state, max_target_seq);
+      succ_off, succ, depth, S, V, 1.0f / T, tokens, position_ids, accept_idx, state, max_target_seq, policy);
   SQ_CHECK_LAUNCH("sq_accept_stochastic(cluster)");
   return SQ_OK;
 }

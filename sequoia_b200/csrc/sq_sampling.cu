@@ -152,6 +152,91 @@ __global__ void __launch_bounds__(NT) sample_level_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sampling WITH replacement (SpecInferTree.py:100-105: softmax(l/T).multinomial(k, replacement=True)) by exact integer
+// inverse-CDF.  Every fp16 probability is an integer multiple of 2^-24, so w = q * 2^24 is an exact uint32 weight, the
+// prefix sums are exact (order-independent) and draw c is the first index whose inclusive prefix exceeds
+// (word_c * total) >> 32.  The oracle's `multinomial_words` does the same arithmetic: given equal q rows the draws agree
+// bit for bit.  The striped row layout (chunk c = i*NT + tid = elements [8c, 8c+8)) is already in index order, so the
+// CDF needs one 4-wide block scan of the per-chunk sums.
+__global__ void __launch_bounds__(NT) sample_replace_kernel(
+    const __half* __restrict__ logits, int64_t ld_logits, const int64_t* __restrict__ words,
+    const int32_t* __restrict__ parent_rows, const int32_t* __restrict__ child_first,
+    const int32_t* __restrict__ n_branch, int k_max, int V, float inv_T, int64_t* __restrict__ positions,
+    int64_t* __restrict__ tokens, const int32_t* __restrict__ state) {
+  __shared__ float red[NW];
+  __shared__ uint32_t wtot[CH][NW];
+  const int j = blockIdx.x;
+  const int prow = parent_rows ? parent_rows[j] : j;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t w[CH * 8];
+  uint32_t cs[CH], excl[CH];
+  {
+    Pack8 x[CH];
+    load_row(logits + prow * ld_logits, V, x);
+    float mx, sum;
+    scale_and_stats(x, inv_T, red, mx, sum);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      cs[i] = 0u;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float q = h2f(softmax_val(x[i].h[e], mx, 0.f, sum));        // fp16 q; padding chunks are exp(-inf) = 0
+        w[i * 8 + e] = (uint32_t)(q * 16777216.f);                        // exact
+        cs[i] += w[i * 8 + e];
+      }
+    }
+  }
+  // inclusive warp scans of the 4 chunk sums, then the warp totals
+  uint32_t inc[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    uint32_t v = cs[i];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    inc[i] = v;
+    if (lane == 31) wtot[i][warp] = v;
+  }
+  __syncthreads();
+  uint32_t total = 0u;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    uint32_t v = wtot[i][lane];                   // NW == 32
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    const uint32_t before = __shfl_sync(0xffffffffu, v, (warp + 31) & 31);   // inclusive total of warps < warp
+    excl[i] = total + (warp ? before : 0u) + inc[i] - cs[i];
+    total += __shfl_sync(0xffffffffu, v, 31);
+  }
+  const int count = n_branch ? n_branch[j] : k_max;
+  const int wbase = child_first ? child_first[j] : j * k_max;
+  const int tbase = tokens ? row_base(state, child_first[j]) : 0;
+  for (int c = 0; c < count; ++c) {
+    const uint32_t word = (uint32_t)words[wbase + c];
+    const uint32_t t = (uint32_t)(((uint64_t)word * (uint64_t)total) >> 32);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (t >= excl[i] && t - excl[i] < cs[i]) {  // unique owner chunk
+        uint32_t run = excl[i];
+        int idx = -1;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          run += w[i * 8 + e];
+          if (idx < 0 && run > t) idx = (i * NT + (int)threadIdx.x) * 8 + e;
+        }
+        if (positions) positions[(int64_t)j * k_max + c] = idx;
+        if (tokens) tokens[tbase + c] = idx;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) residual_kernel(const __half* __restrict__ p, const __half* __restrict__ q,
                                                        __half* __restrict__ out, int V) {
   __shared__ float red[NW];
@@ -233,6 +318,22 @@ extern "C" int sq_sample_level(const sq_half* logits, int64_t ld_logits, const s
                                                                  ld_rand, parent_rows, child_first, n_branch, k_max, V,
                                                                  1.0f / T, mode, positions, tokens, state);
   SQ_CHECK_LAUNCH("sq_sample_level");
+  return SQ_OK;
+}
+
+extern "C" int sq_sample_replace(const sq_half* logits, int64_t ld_logits, const int64_t* words,
+                                 const int32_t* parent_rows, const int32_t* child_first, const int32_t* n_branch,
+                                 int n_parents, int k_max, int V, float T, int64_t* positions, int64_t* tokens,
+                                 const int32_t* state, void* stream) {
+  SQ_CHECK_V(V);
+  if (n_parents == 0 || k_max == 0) return SQ_OK;
+  SQ_CHECK_ARG(words != nullptr, "sq_sample_replace: words required");
+  SQ_CHECK_ARG(tokens == nullptr || (child_first && n_branch), "sq_sample_replace: tokens needs child_first/n_branch");
+  SQ_CHECK_ARG(positions != nullptr || tokens != nullptr, "sq_sample_replace: no output");
+  sample_replace_kernel<<<n_parents, NT, 0, (cudaStream_t)stream>>>((const __half*)logits, ld_logits, words, parent_rows,
+                                                                   child_first, n_branch, k_max, V, 1.0f / T, positions,
+                                                                   tokens, state);
+  SQ_CHECK_LAUNCH("sq_sample_replace");
   return SQ_OK;
 }
 

@@ -113,6 +113,17 @@ def sample_level(logits, rand, n_parents, k_max, T, mode, *, parent_rows=None, c
                               ptr(positions), ptr(tokens), ptr(state), stream_ptr()), "sq_sample_level")
 
 
+def sample_replace(logits, words, n_parents, k_max, T, *, parent_rows=None, child_first=None, n_branch=None,
+                   positions=None, tokens=None, state=None):
+    """i.i.d. draws with replacement from softmax(logits/T) rows (SpecInferTree.py:100-105); words: int64 in [0, 2^32)."""
+    lib = _lib.load()
+    if words.dtype != torch.int64:
+        raise TypeError("sample_replace: words must be int64")
+    check(lib.sq_sample_replace(ptr(logits), logits.stride(-2), ptr(words), ptr(parent_rows), ptr(child_first),
+                                ptr(n_branch), n_parents, k_max, logits.shape[-1], T, ptr(positions), ptr(tokens),
+                                ptr(state), stream_ptr()), "sq_sample_replace")
+
+
 def residual(p, q, out=None):
     _need(p, F16, "residual")
     if out is None:
@@ -129,13 +140,16 @@ def argmax_rows(logits, out=None):
     return out
 
 
+ACCEPT_GE, ACCEPT_KEEP_Q = 1, 2          # sq_accept_stochastic policy bits (include/sequoia_b200.h)
+
+
 def accept_stochastic(target_logits, draft_logits, r, noise, succ_off, succ, depth, S, T, tokens, position_ids,
-                      accept_idx, state, max_target_seq):
+                      accept_idx, state, max_target_seq, policy=0):
     V = target_logits.shape[-1]
     check(_lib.load().sq_accept_stochastic(ptr(target_logits), target_logits.stride(0), ptr(draft_logits),
                                            draft_logits.stride(0), ptr(r), ptr(noise), ptr(succ_off), ptr(succ),
                                            ptr(depth), S, V, T, ptr(tokens), ptr(position_ids), ptr(accept_idx),
-                                           ptr(state), max_target_seq, stream_ptr()), "sq_accept_stochastic")
+                                           ptr(state), max_target_seq, policy, stream_ptr()), "sq_accept_stochastic")
 
 
 def accept_greedy(target_token, succ_off, succ, depth, S, tokens, position_ids, accept_idx, state, max_target_seq):

@@ -102,14 +102,20 @@ class _Static:
         self.mask01 = grow_map["mask"]
 
 
+POLICIES = ("spec", "greedy", "greedys", "specinfer")
+
+
 class _Runtime:
     """Static buffers + captured graphs for one (draft engine, target engine, growmap, policy) combination.
     Lives across prompts (the reference likewise captures its graphs once and reuses them, tests/testbed.py:256-285)."""
 
-    def __init__(self, draft: GraphInferenceEngine, target: GraphInferenceEngineTG, grow_map: dict, greedy: bool,
+    def __init__(self, draft: GraphInferenceEngine, target: GraphInferenceEngineTG, grow_map: dict, policy: str,
                  T: float, top_p: float, M: int, max_target_seq: int, V: int, device):
+        assert policy in POLICIES
         self.draft, self.target, self.grow_map = draft, target, grow_map
-        self.greedy, self.T, self.top_p, self.M, self.max_target_seq, self.V = greedy, float(T), float(top_p), M, max_target_seq, V
+        self.policy = policy
+        self.greedy = policy in ("greedy", "greedys")          # top-k drafting + token-match walk
+        self.T, self.top_p, self.M, self.max_target_seq, self.V = float(T), float(top_p), M, max_target_seq, V
         self.device = torch.device(device)
         dev = self.device
         self.st = _Static(grow_map, dev)
@@ -131,6 +137,11 @@ class _Runtime:
         self.replays: Dict[str, int] = {}
         self.use_graphs = True
         self.external_noise: Optional[torch.Tensor] = None   # tests: (n_iter, V) Exp(1) rows shared with the oracle
+        # policy variants
+        self.tuniform = torch.zeros((S, V), dtype=F16, device=dev) if policy == "greedys" else None
+        self.external_tuniform: Optional[torch.Tensor] = None   # tests: (n_iter, S, V) uniforms shared with the oracle
+        self.words = torch.zeros(S, dtype=torch.int64, device=dev) if policy == "specinfer" else None
+        self.external_words: Optional[torch.Tensor] = None      # tests: (n_iter, S) int64 words in [0, 2^32)
         self.iter = 0
 
     # ---- the op sequences (captured into graphs, or run eagerly in benchmark mode) --------------------------------
@@ -139,6 +150,13 @@ class _Runtime:
 
     def op_sample(self, i: int):
         lv = self.st.levels[i]
+        if self.policy == "specinfer":                 # SpecInferTree.py:100-105: i.i.d. children, with replacement
+            if i == 0 and self.external_words is None:
+                self.words.random_(0, 1 << 32)         # one fresh uniform word per tree node and iteration
+            ops.sample_replace(self.draft_logits, self.words, lv["n_parents"], lv["k"], self.T,
+                               parent_rows=lv["parents"], child_first=lv["first"], n_branch=lv["nb"],
+                               tokens=self.tokens, state=self.state)
+            return
         ops.sample_level(self.draft_logits, None if self.greedy else self.rand, lv["n_parents"], lv["k"], self.T,
                          1 if self.greedy else 0, parent_rows=lv["parents"], child_first=lv["first"], n_branch=lv["nb"],
                          tokens=self.tokens, state=self.state)
@@ -175,7 +193,15 @@ class _Runtime:
     def op_accept(self):
         st = self.st
         if self.greedy:
-            ops.argmax_rows(self.target_logits, self.target_token)                      # GreedyTree.py:186
+            if self.policy == "greedys":                                                # GreedySTree.py:188-190
+                if self.top_p < 1.0:
+                    _top_p_filter_(self.target_logits, self.top_p, self.T)
+                if self.external_tuniform is None:
+                    self.tuniform.uniform_()
+                # softmax(l/T).multinomial(1) per row == the k=1 exponential race of sampling_without_replacement
+                ops.sample_level(self.target_logits, self.tuniform, st.S, 1, self.T, 0, positions=self.target_token)
+            else:
+                ops.argmax_rows(self.target_logits, self.target_token)                  # GreedyTree.py:186
             ops.accept_greedy(self.target_token, st.succ_off, st.succ, st.depth, st.S, self.tokens, self.position_ids,
                               self.accept_idx, self.state, self.max_target_seq)
         else:
@@ -185,7 +211,8 @@ class _Runtime:
                 self.noise.exponential_(1.0)                                            # torch.multinomial's draw
             ops.accept_stochastic(self.target_logits, self.draft_logits, self.r, self.noise, st.succ_off, st.succ,
                                   st.depth, st.S, self.T, self.tokens, self.position_ids, self.accept_idx, self.state,
-                                  self.max_target_seq)
+                                  self.max_target_seq,
+                                  policy=(ops.ACCEPT_GE | ops.ACCEPT_KEEP_Q) if self.policy == "specinfer" else 0)
 
     def op_kv_gather(self):
         md = max(self.st.max_depth, 1)
@@ -282,11 +309,11 @@ def _top_p_filter_(logits: torch.Tensor, top_p: float, T: float):
 _RUNTIMES: Dict[tuple, _Runtime] = {}
 
 
-def get_runtime(draft, target, grow_map, greedy, T, top_p, M, max_target_seq, V, device) -> _Runtime:
-    key = (id(draft), id(target), id(grow_map), bool(greedy), float(T), float(top_p), M, max_target_seq, V)
+def get_runtime(draft, target, grow_map, policy, T, top_p, M, max_target_seq, V, device) -> _Runtime:
+    key = (id(draft), id(target), id(grow_map), policy, float(T), float(top_p), M, max_target_seq, V)
     rt = _RUNTIMES.get(key)
     if rt is None or rt.grow_map is not grow_map:
-        rt = _Runtime(draft, target, grow_map, greedy, T, top_p, M, max_target_seq, V, device)
+        rt = _Runtime(draft, target, grow_map, policy, T, top_p, M, max_target_seq, V, device)
         _RUNTIMES[key] = rt
     return rt
 
@@ -296,7 +323,8 @@ def clear_runtimes():
 
 
 class _TreeBase(Tree):
-    GREEDY = False
+    GREEDY = False          # top-k drafting, no random buffers (GreedyTree / GreedySTree)
+    POLICY = "spec"
 
     def __init__(self, draft_model_engine: GraphInferenceEngine, target_model_engine: GraphInferenceEngineTG,
                  prefix: torch.LongTensor, temperature: float = 0.6, top_p: float = 0.9, draft_kv_len=0,
@@ -321,7 +349,7 @@ class _TreeBase(Tree):
         self.Successors = grow_map["Successors"]
         self.tree_size = grow_map["size"]
         self.initialize(attn_mask, sequence, new_tokens_buffer, parents_buffer, position_ids, None)
-        rt = get_runtime(draft_model_engine, target_model_engine, grow_map, self.GREEDY, temperature, top_p,
+        rt = get_runtime(draft_model_engine, target_model_engine, grow_map, self.POLICY, temperature, top_p,
                          max_length, max_target_seq, vocab_size, device)
         self.rt = rt
         S, M = self.tree_size, max_length
@@ -420,6 +448,8 @@ class _TreeBase(Tree):
                 sample_time += t1
                 compute_time += t2
             return sample_time, compute_time
+        if rt.external_words is not None and rt.words is not None:
+            rt.words.copy_(rt.external_words[rt.iter])
         with torch.inference_mode():
             rt.run("draft", rt.seq_draft)
         self.num_nodes = self.ground_truth_len + self.tree_size - 1
@@ -436,6 +466,8 @@ class _TreeBase(Tree):
         steady = (self.target_kv_len == P - 1)
         if rt.external_noise is not None and not self.GREEDY:
             rt.noise.copy_(rt.external_noise[rt.iter])
+        if rt.external_tuniform is not None and rt.tuniform is not None:
+            rt.tuniform.copy_(rt.external_tuniform[rt.iter])
         if benchmark:
             torch.cuda.synchronize()
             t1 = time.time()
@@ -504,8 +536,24 @@ class _TreeBase(Tree):
 class SpecTree(_TreeBase):
     """Tree/SpecTree.py:7-281 (stochastic Sequoia tree: sampling without replacement + residual verification)."""
     GREEDY = False
+    POLICY = "spec"
 
 
 class GreedyTree(_TreeBase):
     """Tree/GreedyTree.py:6-264 (top-k drafting, argmax verification)."""
     GREEDY = True
+    POLICY = "greedy"
+
+
+class GreedySTree(_TreeBase):
+    """Tree/GreedySTree.py (top-k drafting verified against a target token SAMPLED from softmax(top_p(logits)/T),
+    :188-190): the k=1 exponential race of `sq_sample_level` over the S target rows replaces the row argmax."""
+    GREEDY = True
+    POLICY = "greedys"
+
+
+class SpecInferTree(_TreeBase):
+    """Tree/SpecInferTree.py (the SpecInfer baseline policy on the same tree machinery): children drawn i.i.d. with
+    replacement (`sq_sample_replace`), walk accepts on >= and never masks q (`sq_accept_stochastic` policy bits)."""
+    GREEDY = False
+    POLICY = "specinfer"

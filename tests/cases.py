@@ -76,6 +76,14 @@ DECODE_CASES = {
     "spec_l40_768": ("L40_growmaps/L40-CNN-7b-70b-stochastic.pt", "spec", "draft", "target_gqa", 1024, 31, 128, 2, 17),
 }
 
+# policy variants: GreedySTree (sampled target token) and SpecInferTree (i.i.d. children, >=, no masking)
+VARIANT_CASES = {
+    "greedys_4x4": ("L40_growmaps/4x4-tree.pt", "greedys", "draft", "target", 256, 12, 64, 5, 17),
+    "greedys_same_4x4": ("L40_growmaps/4x4-tree.pt", "greedys", "draft", "draft", 256, 13, 64, 5, 17),
+    "specinfer_8x8": ("L40_growmaps/8x8-tree.pt", "specinfer", "draft", "target", 256, 25, 100, 5, 17),
+    "specinfer_same_8x8": ("L40_growmaps/8x8-tree.pt", "specinfer", "draft", "draft", 256, 26, 80, 5, 17),
+}
+
 _MODELS = {"draft": (CFG_DRAFT, DRAFT_SEED), "target": (CFG_TARGET, TARGET_SEED),
            "target_gqa": (CFG_TARGET_GQA, GQA_SEED)}
 _wcache = {}

@@ -67,8 +67,9 @@ def build_engines(dkey, tkey, M):
     return draft, target
 
 
-def run_decode(name):
-    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = cases.DECODE_CASES[name]
+def run_decode(name, table=None):
+    table = cases.DECODE_CASES if table is None else table
+    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = table[name]
     gm = cases.load_growmap(gm_name)
     draft, target = build_engines(dkey, tkey, M)
     prompt = cases.make_prompt(pseed, plen)
@@ -92,21 +93,29 @@ def run_decode(name):
                                parents_buffer=parents_buffer, position_ids=position_ids,
                                residual_graph=lambda p, q: U.get_residual(p, q), sampling_callables=samp,
                                sample_gather_indices=gather)
+    elif mode == "specinfer":
+        tree = ref.SIT.SpecInferTree(prefix=prompt, device="cpu", temperature=T, top_p=1.0, draft_kv_len=0, target_kv_len=0,
+                                     draft_model_engine=draft, target_model_engine=target, max_length=M, max_target_seq=M,
+                                     grow_map=gm, attn_mask=attn_mask, sequence=sequence,
+                                     new_tokens_buffer=new_tokens_buffer, parents_buffer=parents_buffer,
+                                     position_ids=position_ids, residual_graph=lambda p, q: U.get_residual(p, q),
+                                     sampling_callables=None, sample_gather_indices=gather)
     else:
         samp = {i: (lambda k: (lambda lg: U.sampling_argmax(lg, k)))(max(branches[i])) for i in range(steps - 1)}
-        tree = ref.GT.GreedyTree(prefix=prompt, device="cpu", temperature=T, top_p=1.0, draft_kv_len=0, target_kv_len=0,
+        cls = ref.GST.GreedySTree if mode == "greedys" else ref.GT.GreedyTree
+        tree = cls(prefix=prompt, device="cpu", temperature=T, top_p=1.0, draft_kv_len=0, target_kv_len=0,
                                  draft_model_engine=draft, target_model_engine=target, max_length=M, max_target_seq=M,
                                  grow_map=gm, attn_mask=attn_mask, sequence=sequence, new_tokens_buffer=new_tokens_buffer,
                                  parents_buffer=parents_buffer, position_ids=position_ids,
                                  residual_graph=None, sampling_callables=samp, sample_gather_indices=gather)
     S = gm["size"]
-    rec = {"case": cases.DECODE_CASES[name], "iters": []}
+    rec = {"case": table[name], "iters": []}
     rec["draft_logits0_sha"] = cases.sha(tree.draft_logits[0])
     rec["draft_logits0_head"] = tree.draft_logits[0][:64].clone()
     tot = plen + S - 1
     rec["mask_visible0"] = (tree.attn_mask[:tot, :tot] == 0)             # the window SpecTree built (bool)
     rec["position_ids0"] = tree.position_ids.clone()
-    if mode == "spec":
+    if mode in ("spec", "specinfer"):
         rec["r_sha"] = cases.sha(tree.r)
         rec["rand_sha"] = cases.sha(tree.rand)
     for it in range(iters):
@@ -139,6 +148,12 @@ def gen_decode():
     print("decode_golden.pt", list(out))
 
 
+def gen_variants():
+    out = {name: run_decode(name, cases.VARIANT_CASES) for name in cases.VARIANT_CASES}
+    torch.save(out, os.path.join(HERE, "variants_golden.pt"))
+    print("variants_golden.pt", list(out))
+
+
 def gen_growmaps():
     """Structure goldens for every growmap shipped (tree indices / mask bit-exact): sha of each field."""
     import glob
@@ -155,6 +170,10 @@ def gen_growmaps():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "variants" in sys.argv[1:]:                   # only the policy-variant goldens
+        gen_variants()
+        sys.exit(0)
     gen_utils()
     gen_growmaps()
     gen_decode()
+    gen_variants()

@@ -38,10 +38,12 @@ def load_reference():
     import Engine.Llama_KV as LKV
     import Tree.SpecTree as ST
     import Tree.GreedyTree as GT
+    import Tree.GreedySTree as GST
+    import Tree.SpecInferTree as SIT
     import utils as U
     LMod.LlamaForCausalLM_FI._tied_weights_keys = None
     LMod.LlamaForCausalLM_TG._tied_weights_keys = None
-    return types.SimpleNamespace(LM=LM, EE=EE, LMod=LMod, LKV=LKV, ST=ST, GT=GT, U=U)
+    return types.SimpleNamespace(LM=LM, EE=EE, LMod=LMod, LKV=LKV, ST=ST, GT=GT, GST=GST, SIT=SIT, U=U)
 
 
 def hf_config(cfg):

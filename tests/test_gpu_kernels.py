@@ -287,19 +287,23 @@ def _oracle_engines(dkey, tkey, M):
     return O.EngineOracle(O.LlamaOracle(dcfg, dw, M, "FI")), O.EngineOracle(O.LlamaOracle(tcfg, tw, M, "TG"))
 
 
-@pytest.mark.parametrize("name", ["spec_8x8", "spec_same_8x8", "spec_a100_128"])
+@pytest.mark.parametrize("name", ["spec_8x8", "spec_same_8x8", "spec_a100_128", "specinfer_8x8", "specinfer_same_8x8"])
 def test_accept_walk_stochastic_vs_oracle(name):
     """Feed the kernel exactly the tensors the oracle's verify() saw (raw target logits, draft logits, tokens, r,
-    Exp(1) noise) and compare accept list / bonus / compacted tokens / positions bit-exactly."""
+    Exp(1) noise) and compare accept list / bonus / compacted tokens / positions bit-exactly.  specinfer_*: the
+    SpecInfer walk (>=, q never masked; policy bits of sq_accept_stochastic) against SpecInferTreeOracle."""
     from sequoia_b200.tree import _Static
-    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = cases.DECODE_CASES[name]
+    table = cases.DECODE_CASES if name in cases.DECODE_CASES else cases.VARIANT_CASES
+    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = table[name]
+    ocls = O.SpecInferTreeOracle if mode == "specinfer" else O.SpecTreeOracle
+    policy = 3 if mode == "specinfer" else 0
     gm = cases.load_growmap(gm_name)
     S = gm["size"]
     draft, target = _oracle_engines(dkey, tkey, M)
     torch.manual_seed(rng_seed)
     noise = torch.empty(iters, cases.V, dtype=F16).exponential_(1.0)
-    tree = O.SpecTreeOracle(draft, target, cases.make_prompt(pseed, plen), gm, temperature=0.6, top_p=1.0, max_length=M,
-                            bonus_noise=noise)
+    tree = ocls(draft, target, cases.make_prompt(pseed, plen), gm, temperature=0.6, top_p=1.0, max_length=M,
+                bonus_noise=noise)
     st = _Static(gm, DEV)
     for it in range(iters):
         P = tree.ground_truth_len
@@ -315,7 +319,7 @@ def test_accept_walk_stochastic_vs_oracle(name):
         state = torch.zeros(16, dtype=torch.int32, device=DEV)
         state[0] = P
         ops().accept_stochastic(tl_in.to(DEV), dl_in.to(DEV), tree.r.to(DEV), noise[it].to(DEV), st.succ_off, st.succ,
-                                st.depth, S, 0.6, d_tokens, d_pos, acc, state, M)
+                                st.depth, S, 0.6, d_tokens, d_pos, acc, state, M, policy=policy)
         hs = state.cpu()
         n_new = int(hs[3])
         got_list = list(range(P)) + acc[:n_new].cpu().tolist()
@@ -328,6 +332,85 @@ def test_accept_walk_stochastic_vs_oracle(name):
             assert torch.equal(d_pos.cpu(), tree.position_ids)
         if terminal:
             break
+
+
+def test_accept_policy_bits_change_the_walk():
+    """>= vs > on an exact tie (r = 0 and q[tok] > 0 = p[tok]... here p[tok] == r*q[tok] == 0): the SpecTree walk
+    rejects, the SpecInfer walk accepts; unknown bits are refused."""
+    from sequoia_b200.tree import _Static
+    gm = cases.load_growmap("L40_growmaps/2-chain.pt")
+    S, V, P = gm["size"], cases.V, 10
+    st = _Static(gm, DEV)
+    tl = torch.zeros(S, V, dtype=F16)
+    tl[:, 5] = 30.0                       # p = one-hot on token 5 -> p[7] == 0 exactly
+    dl = torch.zeros(S, V, dtype=F16)
+    tokens = torch.zeros(64, dtype=torch.long)
+    tokens[:P] = torch.arange(3, 3 + P)
+    tokens[P] = 7                         # the single child proposes token 7
+    r = torch.zeros(64, dtype=F16)        # r = 0 -> threshold r*q == 0 == p[7]
+    noise = torch.ones(V, dtype=F16)
+    out = {}
+    for policy in (0, 3):
+        d_tokens, d_pos = tokens.to(DEV), torch.arange(64).to(DEV)
+        acc = torch.zeros(8, dtype=torch.int32, device=DEV)
+        state = torch.zeros(16, dtype=torch.int32, device=DEV)
+        state[0] = P
+        ops().accept_stochastic(tl.to(DEV), dl.to(DEV), r.to(DEV), noise.to(DEV), st.succ_off, st.succ, st.depth, S, 1.0,
+                                d_tokens, d_pos, acc, state, 64, policy=policy)
+        out[policy] = int(state.cpu()[3])
+    assert out[0] == 0 and out[3] == 1
+    with pytest.raises(Exception):
+        ops().accept_stochastic(tl.to(DEV), dl.to(DEV), r.to(DEV), noise.to(DEV), st.succ_off, st.succ, st.depth, S, 1.0,
+                                tokens.to(DEV), torch.arange(64).to(DEV), torch.zeros(8, dtype=torch.int32, device=DEV),
+                                torch.zeros(16, dtype=torch.int32, device=DEV), 64, policy=8)
+
+
+# ------------------------------------------------------------------------------------------------ sampling with replacement
+@pytest.mark.parametrize("rows,k,peaked", [(1, 8, False), (19, 13, False), (34, 6, True), (8, 32, True)])
+def test_sample_replace_matches_integer_cdf(rows, k, peaked):
+    """sq_sample_replace vs the oracle's exact integer inverse-CDF on the SAME fp16 probabilities (the kernel's own
+    softmax, read back through sq_softmax_T): bit-exact, every draw."""
+    logits, _ = cases.sampling_case(40 + rows, rows, peaked)
+    g = torch.Generator().manual_seed(rows * 100 + k)
+    words = torch.randint(0, 1 << 32, (rows, k), generator=g, dtype=torch.int64)
+    words[0, 0] = 0
+    words[-1, -1] = (1 << 32) - 1
+    d_logits = logits.to(DEV)
+    q = ops().softmax_T(d_logits, 0.6).cpu()
+    want = O.multinomial_words(q, words)
+    pos = torch.full((rows * k,), -1, dtype=torch.int64, device=DEV)
+    ops().sample_replace(d_logits, words.to(DEV).reshape(-1), rows, k, 0.6, positions=pos)
+    assert torch.equal(pos.cpu().view(rows, k), want)
+    # the draws follow q: the empirical law of many draws from row 0 is close to q[0] in total variation
+    n = 4096
+    w2 = torch.randint(0, 1 << 32, (1, n), generator=g, dtype=torch.int64)
+    pos2 = torch.empty(n, dtype=torch.int64, device=DEV)
+    ops().sample_replace(d_logits[:1], w2.to(DEV).reshape(-1), 1, n, 0.6, positions=pos2)
+    assert torch.equal(pos2.cpu().view(1, n), O.multinomial_words(q[:1], w2))
+
+
+def test_sample_replace_tree_level_addressing():
+    """Tree addressing (parent_rows / child_first / n_branch / tokens / state) == per-node words, per-parent draws."""
+    gm = cases.load_growmap("L40_growmaps/8x8-tree.pt")
+    from sequoia_b200.tree import _Static
+    st = _Static(gm, DEV)
+    S, P, V = gm["size"], 37, cases.V
+    logits, _ = cases.sampling_case(91, S, False)
+    g = torch.Generator().manual_seed(4)
+    words = torch.randint(0, 1 << 32, (S,), generator=g, dtype=torch.int64)
+    state = torch.zeros(16, dtype=torch.int32, device=DEV)
+    state[0] = P
+    tokens = torch.zeros(256, dtype=torch.int64, device=DEV)
+    d_logits = logits.to(DEV)
+    q = ops().softmax_T(d_logits, 0.6).cpu()
+    for lv in st.levels:
+        ops().sample_replace(d_logits, words.to(DEV), lv["n_parents"], lv["k"], 0.6, parent_rows=lv["parents"],
+                             child_first=lv["first"], n_branch=lv["nb"], tokens=tokens, state=state)
+    got = tokens.cpu()
+    for parent, ch in enumerate(gm["Successors"]):
+        for c in ch:
+            want = int(O.multinomial_words(q[parent:parent + 1], words[c].view(1, 1)))
+            assert int(got[P - 1 + c]) == want, (parent, c)
 
 
 # ------------------------------------------------------------------------------------------------ engine forward

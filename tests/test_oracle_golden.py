@@ -60,17 +60,26 @@ def _oracle_engines(dkey, tkey, M):
     return (O.EngineOracle(O.LlamaOracle(dcfg, dw, M, "FI")), O.EngineOracle(O.LlamaOracle(tcfg, tw, M, "TG")))
 
 
-@pytest.mark.parametrize("name", list(cases.DECODE_CASES))
+VAR = torch.load(os.path.join(G, "variants_golden.pt"))
+ALL_CASES = dict(cases.DECODE_CASES, **cases.VARIANT_CASES)
+
+
+@pytest.mark.parametrize("name", list(ALL_CASES))
 def test_decode_trace(name):
-    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = cases.DECODE_CASES[name]
-    rec = DEC[name]
+    """Oracle == unmodified reference, step by step (SpecTree / GreedyTree and the GreedySTree / SpecInferTree policy
+    variants), sharing one CPU RNG seed so that every torch draw lines up."""
+    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = ALL_CASES[name]
+    rec = DEC[name] if name in DEC else VAR[name]
     gm = cases.load_growmap(gm_name)
     draft, target = _oracle_engines(dkey, tkey, M)
     prompt = cases.make_prompt(pseed, plen)
     torch.manual_seed(rng_seed)
-    if mode == "spec":
-        tree = O.SpecTreeOracle(draft, target, prompt, gm, temperature=0.6, top_p=1.0, max_length=M)
+    if mode in ("spec", "specinfer"):
+        cls = O.SpecTreeOracle if mode == "spec" else O.SpecInferTreeOracle
+        tree = cls(draft, target, prompt, gm, temperature=0.6, top_p=1.0, max_length=M)
         assert cases.sha(tree.r) == rec["r_sha"] and cases.sha(tree.rand) == rec["rand_sha"]
+    elif mode == "greedys":
+        tree = O.GreedySTreeOracle(draft, target, prompt, gm, temperature=0.6, top_p=1.0, max_length=M)
     else:
         tree = O.GreedyTreeOracle(draft, target, prompt, gm, max_length=M)
     S = gm["size"]
@@ -88,7 +97,7 @@ def test_decode_trace(name):
         valid, a, _, terminal = tree.verify()
         assert a == g["accept_len"] and terminal == g["terminal"]
         assert torch.equal(valid, g["valid_tokens"])
-        if mode == "spec":
+        if mode in ("spec", "specinfer", "greedys"):
             assert cases.sha(tree.target_logits) == g["target_logits_sha"]
         assert cases.sha(draft.kv_cache.k_cache) == g["draft_k_sha"]
         assert cases.sha(draft.kv_cache.v_cache) == g["draft_v_sha"]
