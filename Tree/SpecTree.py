@@ -1,2 +1,2 @@
-"""Drop-in for the reference's Tree/SpecTree.py import path (tests/testbed.py:14)."""
-from sequoia_b200.tree import SpecTree  # noqa: F401
+"""Drop-in for the reference's Tree/SpecTree.py import path (tests/testbed.py, tests/test_accept.py)."""
+from sequoia_b200.tree import SpecTree, SpecTreeTest  # noqa: F401

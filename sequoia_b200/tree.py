@@ -102,7 +102,7 @@ class _Static:
         self.mask01 = grow_map["mask"]
 
 
-POLICIES = ("spec", "greedy", "greedys", "specinfer")
+POLICIES = ("spec", "greedy", "greedys", "specinfer", "spec_test")
 
 
 class _Runtime:
@@ -212,7 +212,8 @@ class _Runtime:
             ops.accept_stochastic(self.target_logits, self.draft_logits, self.r, self.noise, st.succ_off, st.succ,
                                   st.depth, st.S, self.T, self.tokens, self.position_ids, self.accept_idx, self.state,
                                   self.max_target_seq,
-                                  policy=(ops.ACCEPT_GE | ops.ACCEPT_KEEP_Q) if self.policy == "specinfer" else 0)
+                                  policy={"specinfer": ops.ACCEPT_GE | ops.ACCEPT_KEEP_Q,
+                                          "spec_test": ops.ACCEPT_GE}.get(self.policy, 0))
 
     def op_kv_gather(self):
         md = max(self.st.max_depth, 1)
@@ -360,8 +361,9 @@ class _TreeBase(Tree):
         self.position_ids = rt.position_ids
         self.storage_ids = rt.storage_ids
         self.draft_logits = rt.draft_logits
+        prefix_dev = prefix.to(self.device).clone()    # `prefix` may be a view of rt.tokens (a previous verify's valid_tokens)
         self.tokens.zero_()
-        self.tokens[:P] = prefix.to(self.device)
+        self.tokens[:P] = prefix_dev
         self.num_nodes = P
         self.ground_truth_len = P
         if not self.GREEDY:
@@ -557,3 +559,62 @@ class SpecInferTree(_TreeBase):
     replacement (`sq_sample_replace`), walk accepts on >= and never masks q (`sq_accept_stochastic` policy bits)."""
     GREEDY = False
     POLICY = "specinfer"
+
+
+# ---- acceptance-rate measurement trees (Tree/SpecTree.py:284-483 SpecTreeTest, Tree/GreedyTree.py:264-456 GreedyTreeTest) ----
+_STARS: Dict[int, dict] = {}
+
+
+def star_grow_map(width: int) -> dict:
+    """Root + `width` children: the one-level tree the reference's *TreeTest classes hard-code (`Successors =
+    [list(range(1, W+1))] + [[]]*W`, SpecTree.py:312-313), as a growmap so that the same kernels / graphs serve it."""
+    gm = _STARS.get(width)
+    if gm is None:
+        S = width + 1
+        mask = torch.eye(S, dtype=torch.long)
+        mask[:, 0] = 1
+        gm = {"roots": [[0], list(range(1, S))], "branches": [[width], [0] * width],
+              "Successors": [list(range(1, S))] + [[] for _ in range(width)], "mask": mask,
+              "depth": torch.LongTensor([0] + [1] * width), "size": S}
+        _STARS[width] = gm
+    return gm
+
+
+class _StarTest(_TreeBase):
+    """One decode step of the acceptance-rate experiment (tests/test_accept.py:36-86): draft `max_width` children of the
+    last committed token, verify, report WHICH child (rank b, or -1) was accepted.  Like the reference, a new object is
+    built per step with the KV lengths the previous verify returned; its constructor already drafts the children."""
+
+    def __init__(self, draft_model_engine, target_model_engine, prefix, temperature: float = 0.6, top_p: float = 0.9,
+                 draft_kv_len=0, target_kv_len=0, max_length=256, max_width=32, device: str = "cpu", grow_map=None,
+                 attn_mask=None, sequence=None, new_tokens_buffer=None, parents_buffer=None, position_ids=None) -> None:
+        self.max_width = max_width
+        super().__init__(draft_model_engine, target_model_engine, prefix, temperature=temperature, top_p=top_p,
+                         draft_kv_len=draft_kv_len, target_kv_len=target_kv_len, max_length=max_length, device=device,
+                         max_target_seq=max_length, vocab_size=draft_model_engine.engine.model_config.vocab_size,
+                         grow_map=star_grow_map(max_width), attn_mask=attn_mask, sequence=sequence,
+                         new_tokens_buffer=new_tokens_buffer, parents_buffer=parents_buffer, position_ids=position_ids)
+        self.construct_grow_map()                       # SpecTree.py:342 / GreedyTree.py:322
+
+    @torch.inference_mode()
+    def verify(self, benchmark=False):
+        """-> (valid_tokens, len(accept_list), len(accept_list), b, terminal)   (SpecTree.py:470-479)"""
+        valid, a, _, terminal = super().verify(benchmark=False)
+        hs = self.rt.host_state
+        n_new, P_old = int(hs[3]), int(hs[4])
+        b = int(self.rt.accept_idx[0]) - (P_old - 1) - 1 if n_new > 0 else -1     # successor order of the accepted child
+        return valid, a, a, b, terminal
+
+
+class SpecTreeTest(_StarTest):
+    """Tree/SpecTree.py:284-483: children by sampling without replacement, accept on >= with the rejected token masked
+    out of q.  Same estimator as the reference; arithmetic is the SpecTree kernels' fp16 chain (the reference's Test
+    class happens to hold r / rand in fp32)."""
+    GREEDY = False
+    POLICY = "spec_test"
+
+
+class GreedyTreeTest(_StarTest):
+    """Tree/GreedyTree.py:264-456: top-`max_width` children, accept the one equal to the target's argmax."""
+    GREEDY = True
+    POLICY = "greedy"

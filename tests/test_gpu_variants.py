@@ -158,3 +158,88 @@ def test_specinfer_tree_lockstep(name, graphs):
         target.clear_kv()
     assert matched >= 1, f"{name}: not a single iteration matched the oracle"
     assert draft.engine.runner.plan.error() == 0 and target.engine.runner.plan.error() == 0
+
+
+# ---- acceptance-rate measurement trees (SpecTreeTest / GreedyTreeTest, per-step construction like tests/test_accept.py) ----
+def _test_loop(cls, draft, target, prompt, M, W, steps, T=0.6, top_p=1.0):
+    bufs = _buffers(M)
+    ids = prompt.to(DEV)
+    dkv = tkv = 0
+    out = []
+    for _ in range(steps):
+        tree = cls(prefix=ids, device=DEV, temperature=T, top_p=top_p, draft_kv_len=dkv, target_kv_len=tkv,
+                   draft_model_engine=draft, target_model_engine=target, max_length=M, max_width=W, **bufs)
+        P = tree.ground_truth_len
+        children = tree.tokens[P:P + W].clone()
+        valid, dkv, tkv, b, terminal = tree.verify(benchmark=True)
+        out.append(dict(P=P, children=children.cpu(), valid=valid.clone().cpu(), a=dkv, b=b, terminal=terminal,
+                        target_token0=int(tree.rt.target_token[0]) if tree.GREEDY else None))
+        ids = valid.clone()
+        if terminal:
+            break
+    draft.clear_kv()
+    target.clear_kv()
+    return out
+
+
+def test_greedy_tree_test_reports_accepted_rank():
+    """GreedyTreeTest (GreedyTree.py:264-456): b == rank of the target's argmax among the drafted top-W children (or -1),
+    returned lengths feed the next construction, and the decoded stream equals plain GreedyTree decoding."""
+    from Tree.GreedyTree import GreedyTree, GreedyTreeTest
+    M, W, steps = 256, 8, 8
+    prompt = cases.make_prompt(41, 48)
+    draft, target = _engines("draft", "target", M)
+    rows = _test_loop(GreedyTreeTest, draft, target, prompt, M, W, steps)
+    assert len(rows) >= 4
+    for r in rows:
+        ch = r["children"].tolist()
+        want_b = ch.index(r["target_token0"]) if r["target_token0"] in ch else -1
+        assert r["b"] == want_b
+        assert r["a"] == r["P"] + (1 if want_b >= 0 else 0)
+        if not r["terminal"]:
+            assert r["valid"].shape[0] == r["a"] + 1
+            if want_b >= 0:
+                assert int(r["valid"][-2]) == ch[want_b]
+    stream = rows[-1]["valid"]
+    # same prompt through the ordinary GreedyTree: greedy speculative decoding is lossless -> same token stream
+    gm = cases.load_growmap("L40_growmaps/4x4-tree.pt")
+    tree = GreedyTree(prefix=prompt, device=DEV, temperature=0.6, top_p=1.0, draft_kv_len=0, target_kv_len=0,
+                      draft_model_engine=draft, target_model_engine=target, max_length=M, max_target_seq=M, grow_map=gm,
+                      residual_graph=None, sampling_callables=None, sample_gather_indices=None, **_buffers(M))
+    valid = None
+    while valid is None or valid.shape[0] < stream.shape[0]:
+        tree.construct_grow_map()
+        valid, _, _, term = tree.verify()
+        if term:
+            break
+    n = min(valid.shape[0], stream.shape[0])
+    new = n - prompt.shape[0]
+    agree = int((valid[:n].cpu() == stream[:n]).sum()) - prompt.shape[0]
+    draft.clear_kv()
+    target.clear_kv()
+    assert new >= 4 and agree >= new - 1, f"{agree}/{new} new tokens agree (fp16 near-ties may flip at most one)"
+
+
+def test_spec_tree_test_same_model_accepts_first_child():
+    """SpecTreeTest (SpecTree.py:284-483) with draft == target weights: p ~= q, so p[tok] >= r*q[tok] holds for the first
+    child almost surely -> b == 0; structure of the returned tuple as the reference's (5-tuple, lengths, rank)."""
+    from Tree.SpecTree import SpecTreeTest
+    M, W, steps = 256, 8, 8
+    prompt = cases.make_prompt(42, 48)
+    draft, target = _engines("draft", "draft", M)
+    torch.manual_seed(3)
+    rows = _test_loop(SpecTreeTest, draft, target, prompt, M, W, steps)
+    assert len(rows) >= 4
+    for r in rows:
+        assert -1 <= r["b"] < W
+        assert r["a"] == r["P"] + (1 if r["b"] >= 0 else 0)
+        if not r["terminal"]:
+            assert r["valid"].shape[0] == r["a"] + 1
+            if r["b"] >= 0:
+                assert int(r["valid"][-2]) == int(r["children"][r["b"]])
+        assert len(set(r["children"].tolist())) == W          # drawn WITHOUT replacement
+    assert sum(1 for r in rows if r["b"] == 0) >= len(rows) - 1
+    # different models (random weights): mostly nothing accepted, and b spreads over [-1, W)
+    draft2, target2 = _engines("draft", "target", M)
+    rows2 = _test_loop(SpecTreeTest, draft2, target2, prompt, M, W, steps)
+    assert all(-1 <= r["b"] < W for r in rows2)
