@@ -90,3 +90,24 @@ def test_large_search_is_fast():
     assert time.time() - t0 < 60
     g = ts.build_grow_map(table, 256, 16)
     assert g["size"] == 256
+
+
+def test_searched_growmaps_load_into_the_runtime_tables():
+    """What tree_search produces is what the decode runtime consumes: `_Static` (CSR successors, per-level parents /
+    first-child / branch tables, packed ancestor bits) accepts every searched growmap, the shipped B200 one and the
+    star growmap of the acceptance-rate trees; the packed bits reproduce the mask."""
+    from sequoia_b200.tree import _Static, pack_tree_mask, star_grow_map
+    root = os.path.dirname(HERE)
+    maps = [c["grow_map"] for c in GOLD["cases"].values()]
+    maps.append(torch.load(os.path.join(root, "B200_growmaps", "68m_7b-demo_acceptance.pt")))
+    maps.append(star_grow_map(32))
+    for gm in maps:
+        st = _Static(gm, "cpu")
+        S = gm["size"]
+        assert st.S == S and st.succ_off.numel() == S + 1 and int(st.succ_off[-1]) == S - 1
+        assert sum(lv["tb"] for lv in st.levels) == S - 1
+        bits = pack_tree_mask(gm["mask"])
+        for r in range(S):
+            row = [(int(bits[r, c // 32]) >> (c % 32)) & 1 for c in range(S)]
+            assert row == gm["mask"][r].tolist()
+        assert st.max_depth == int(gm["depth"].max())
