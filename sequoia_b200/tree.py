@@ -303,7 +303,7 @@ def _top_p_filter_(logits: torch.Tensor, top_p: float, T: float):
     filt[..., 1:] = filt[..., :-1].clone()
     filt[..., 0] = 0
     indices_to_remove = filt.scatter(-1, sorted_indices, filt)
-    logits[indices_to_remove] = float("-inf")
+    logits.masked_fill_(indices_to_remove, float("-inf"))     # (boolean-index assignment would sync: not capturable)
     return logits
 
 

@@ -243,3 +243,54 @@ def test_spec_tree_test_same_model_accepts_first_child():
     draft2, target2 = _engines("draft", "target", M)
     rows2 = _test_loop(SpecTreeTest, draft2, target2, prompt, M, W, steps)
     assert all(-1 <= r["b"] < W for r in rows2)
+
+
+@pytest.mark.parametrize("graphs", [True, False])
+def test_spec_tree_with_top_p_filter(graphs):
+    """top_p < 1 (get_sampling_logits, utils.py:65-77 — off in every named configuration, on by default in the
+    reference's CLI): the nucleus filter runs inside the captured verify graph; lock-step with the oracle."""
+    from Tree.SpecTree import SpecTree
+    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = cases.DECODE_CASES["spec_same_8x8"]
+    gm = cases.load_growmap(gm_name)
+    prompt = cases.make_prompt(pseed, plen)
+    od, ot = _oracles(dkey, tkey, M)
+    noise = torch.empty(iters, cases.V, dtype=F16).exponential_(1.0, generator=torch.Generator().manual_seed(5))
+    torch.manual_seed(rng_seed)
+    otree = O.SpecTreeOracle(od, ot, prompt, gm, temperature=0.6, top_p=0.9, max_length=M, bonus_noise=noise)
+    draft, target = _engines(dkey, tkey, M)
+    torch.manual_seed(rng_seed)
+    tree = SpecTree(prefix=prompt, device=DEV, temperature=0.6, top_p=0.9, draft_kv_len=0, target_kv_len=0,
+                    draft_model_engine=draft, target_model_engine=target, max_length=M, max_target_seq=M, grow_map=gm,
+                    residual_graph=None, sampling_callables=None, sample_gather_indices=None, **_buffers(M))
+    tree.rt.use_graphs = graphs
+    tree.rt.external_noise = noise.to(DEV)
+    S = gm["size"]
+    matched = 0
+    try:
+        for it in range(iters):
+            P = tree.ground_truth_len
+            otree.construct_grow_map()
+            tree.construct_grow_map()
+            got = tree.tokens[P:P + S - 1].cpu()
+            if not torch.equal(got, otree.tokens[P:P + S - 1]):
+                ok, why = _explained_tree_mismatch(otree, got, P, gm, "spec")
+                assert ok, why
+                break
+            ov, oa, _, oterm = otree.verify()
+            valid, a, _, terminal = tree.verify()
+            # the filter really removed mass: some target probabilities are exactly 0 in the oracle
+            assert bool((otree.target_logits == 0).any())
+            if tree.accept_list() != otree.last_trace.accept_list:
+                ok, why = _explained_accept_mismatch(otree, tree.accept_list(), otree.last_trace.accept_list, gm, "spec", P)
+                assert ok, why
+                break
+            assert (a, terminal) == (oa, oterm) and torch.equal(valid.cpu(), ov)
+            matched += 1
+            if terminal:
+                break
+    finally:
+        tree.rt.external_noise = None
+        tree.rt.use_graphs = True
+        draft.clear_kv()
+        target.clear_kv()
+    assert matched >= 1
