@@ -82,6 +82,7 @@ def _tree_class(name: str):
     return cls
 
 
+@torch.inference_mode()
 def simulation(target, draft, prompts, grow_map, tree_cls, T, top_p, M, benchmark: bool):
     """simulation_fast / simulation_benchmark."""
     bufs = _buffers(M)
@@ -141,6 +142,7 @@ def simulation(target, draft, prompts, grow_map, tree_cls, T, top_p, M, benchmar
                 tokens_per_second=decoded / total_time if total_time > 0 else 0.0)
 
 
+@torch.inference_mode()          # engine outputs are inference tensors; the nucleus filter edits them in place
 def simulation_baseline(target, prompts, T, top_p, M, new_tokens: int = 32):
     """Autoregressive sampling from the target alone (tests/testbed.py:98-137)."""
     from utils import _make_causal_mask, get_sampling_logits
