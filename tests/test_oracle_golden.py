@@ -110,3 +110,29 @@ def test_decode_trace(name):
             tot = n + S - 1
             assert torch.equal(tree.attn_mask[:tot, :tot] == 0, g["mask_visible_next"])
             assert torch.equal(O.visible_from_rule(M, n, gm["mask"]), g["mask_visible_next"])
+
+
+def test_multinomial_words_is_an_exact_inverse_cdf_sampler():
+    """The integer inverse-CDF used for SpecInfer-style draws (oracle + sq_sample_replace): every draw lands on a token
+    with q > 0, the extreme words hit the first / last support token, and the empirical law follows q."""
+    g = torch.Generator().manual_seed(3)
+    q = torch.softmax((torch.randn(2, 512, generator=g) * 3).half() / 0.6, dim=-1)
+    q[1, :100] = 0                                                    # leading zero-probability tokens
+    words = torch.tensor([[0, (1 << 32) - 1], [0, (1 << 32) - 1]])
+    ends = O.multinomial_words(q, words)
+    for r in range(2):
+        nz = (q[r] > 0).nonzero().flatten()
+        assert int(ends[r, 0]) == int(nz[0]) and int(ends[r, 1]) == int(nz[-1])
+    n = 200_000
+    w = torch.randint(0, 1 << 32, (2, n), generator=g, dtype=torch.int64)
+    idx = O.multinomial_words(q, w)
+    for r in range(2):
+        assert bool((q[r][idx[r]] > 0).all())
+        emp = torch.bincount(idx[r], minlength=512).double() / n
+        ref = q[r].double() / q[r].double().sum()
+        assert float((emp - ref).abs().sum()) < 0.06                  # total variation*2 of a 200k-sample histogram
+    # same answer as a float64 inverse CDF away from the boundaries
+    cdf = (q[0].double() / q[0].double().sum()).cumsum(0)
+    u = (w[0, :2000].double() + 0.5) / 4294967296.0
+    f64 = torch.searchsorted(cdf, u, right=True).clamp(max=511)
+    assert float((f64 == idx[0, :2000]).double().mean()) > 0.995
