@@ -84,6 +84,17 @@ VARIANT_CASES = {
     "specinfer_same_8x8": ("L40_growmaps/8x8-tree.pt", "specinfer", "draft", "draft", 256, 26, 80, 5, 17),
 }
 
+# reference sweep shapes (tests/run.sh: K chains of length L, driven there through SpecInferTree); oracle-vs-reference only
+SWEEP_CASES = {
+    "sweep_specinfer_8x1": ("L40_growmaps/8x1-tree.pt", "specinfer", "draft", "target", 256, 51, 64, 3, 17),
+    "sweep_specinfer_1x8": ("L40_growmaps/1x8-tree.pt", "specinfer", "draft", "draft", 256, 52, 64, 3, 17),
+    "sweep_specinfer_2x32": ("L40_growmaps/2x32-tree.pt", "specinfer", "draft", "draft", 256, 53, 64, 3, 17),
+    "sweep_specinfer_128x1": ("L40_growmaps/128x1-tree.pt", "specinfer", "draft", "target", 384, 54, 64, 3, 17),
+    "sweep_spec_16x8": ("L40_growmaps/16x8-tree.pt", "spec", "draft", "target", 384, 55, 64, 3, 17),
+    "sweep_greedy_1x128": ("L40_growmaps/1x128-tree.pt", "greedy", "draft", "draft", 384, 56, 64, 2, 17),
+    "sweep_greedys_5x8": ("L40_growmaps/5x8-tree.pt", "greedys", "draft", "draft", 256, 57, 64, 3, 17),
+}
+
 _MODELS = {"draft": (CFG_DRAFT, DRAFT_SEED), "target": (CFG_TARGET, TARGET_SEED),
            "target_gqa": (CFG_TARGET_GQA, GQA_SEED)}
 _wcache = {}

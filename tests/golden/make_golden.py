@@ -154,6 +154,12 @@ def gen_variants():
     print("variants_golden.pt", list(out))
 
 
+def gen_sweep():
+    out = {name: run_decode(name, cases.SWEEP_CASES) for name in cases.SWEEP_CASES}
+    torch.save(out, os.path.join(HERE, "sweep_golden.pt"))
+    print("sweep_golden.pt", list(out))
+
+
 def gen_growmaps():
     """Structure goldens for every growmap shipped (tree indices / mask bit-exact): sha of each field."""
     import glob
@@ -170,10 +176,14 @@ def gen_growmaps():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    if "variants" in sys.argv[1:]:                   # only the policy-variant goldens
-        gen_variants()
+    if "variants" in sys.argv[1:] or "sweep" in sys.argv[1:]:   # only the policy-variant / sweep-shape goldens
+        if "variants" in sys.argv[1:]:
+            gen_variants()
+        if "sweep" in sys.argv[1:]:
+            gen_sweep()
         sys.exit(0)
     gen_utils()
     gen_growmaps()
     gen_decode()
     gen_variants()
+    gen_sweep()

@@ -61,7 +61,8 @@ def _oracle_engines(dkey, tkey, M):
 
 
 VAR = torch.load(os.path.join(G, "variants_golden.pt"))
-ALL_CASES = dict(cases.DECODE_CASES, **cases.VARIANT_CASES)
+VAR.update(torch.load(os.path.join(G, "sweep_golden.pt")))
+ALL_CASES = dict(cases.DECODE_CASES, **cases.VARIANT_CASES, **cases.SWEEP_CASES)
 
 
 @pytest.mark.parametrize("name", list(ALL_CASES))
