@@ -173,6 +173,11 @@ int sq_accept_greedy(const int64_t* target_token, const int32_t* succ_off, const
                      const int32_t* depth, int S, int64_t* tokens, int64_t* position_ids, int32_t* accept_idx,
                      int32_t* state, int max_target_seq, void* stream);
 
+/* ---- L2 prefetch of upcoming weights (no reference counterpart; a hint, never changes results) ----
+ * Issues cp.async.bulk.prefetch.L2 for the panel base[r*pitch + off, + seg) of rows r < rows (all in bytes, multiples
+ * of 16).  Meant for a forked stream next to the latency-bound kernels between two weight GEMMs. */
+int sq_l2_prefetch(const void* base, int64_t pitch_bytes, int rows, int64_t off_bytes, int64_t seg_bytes, void* stream);
+
 /* ---- weight-streaming GEMM for <= 128 rows (nn.Linear, Llama_modules.py:108-110,138,270-272; Llama_model.py:213) ---- */
 
 /* C[n, N] = A[n, K] * W[N, K]^T, fp16 in / fp32 accumulate / fp16 out, n <= 128.  A: (n_max, lda), W: (N, K) row-major

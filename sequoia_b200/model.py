@@ -236,6 +236,39 @@ class LlamaRunner:
             from .peer import PeerBuffers
             self.peer = PeerBuffers(tp_group, self.device, n, h)
         self.attn_impl = int(os.environ.get("SQ_ATTN_IMPL", "0"))
+        # L2 prefetch of the next GEMM's weights while the latency-bound kernels between two GEMMs leave HBM idle
+        # (csrc/sq_prefetch.cu).  SQ_L2_PREFETCH = "A,B,C,D" MB budgets for the four windows of a layer (after qkv /
+        # o_proj / gate_up / down_proj), "0" = off.  A hint only: results are identical with or without it.
+        pf = os.environ.get("SQ_L2_PREFETCH", "0")
+        self.pf_budget = None
+        if pf not in ("0", "") and self.peer is None and h >= 2048:      # pointless for the small draft models
+            vals = [74, 24, 28, 28] if pf == "1" else [float(x) for x in pf.split(",")]
+            assert len(vals) == 4, "SQ_L2_PREFETCH: 1 | 0 | A,B,C,D (MB)"
+            self.pf_budget = [int(v * 1e6) for v in vals]
+            self.pf_stream = torch.cuda.Stream(device=self.device)
+
+    def _prefetch(self, window: int, weights):
+        """Fork: on the side stream, pull the leading columns of `weights` (in order, until the window's byte budget is
+        spent) into L2.  Joined by `_prefetch_join` before the next GEMM."""
+        if self.pf_budget is None:
+            return
+        left = self.pf_budget[window]
+        cur = torch.cuda.current_stream()
+        self.pf_stream.wait_stream(cur)
+        with torch.cuda.stream(self.pf_stream):
+            for w, col0 in weights:
+                row_bytes = w.shape[0] * w.element_size()
+                cols = min((left // row_bytes) // 64 * 64, w.shape[1] - col0)
+                if cols <= 0:
+                    continue
+                ops.l2_prefetch(w, col0, col0 + cols)
+                left -= cols * row_bytes
+        self._pf_fork = True
+
+    def _prefetch_join(self):
+        if self.pf_budget is not None and getattr(self, "_pf_fork", False):
+            torch.cuda.current_stream().wait_stream(self.pf_stream)
+            self._pf_fork = False
 
     def _plan(self, a, w, c):
         try:
@@ -272,7 +305,10 @@ class LlamaRunner:
         ops.embed_rows(self.embed, tokens, n, self.hidden, state=state, n0=n0)
         ops.rmsnorm(self.hidden, self.layers[0]["ln1"], self.normed, n, self.eps)
         for l, ly in enumerate(self.layers):
+            self._prefetch_join()
             self._linear(l, "qkv", self.normed, ly["wqkv"], self.qkv, n)
+            if self.pf_budget is not None:          # window A: RoPE + attention
+                self._prefetch(0, [(ly["wo"], 0), (ly["wgu"], 0)])
             ops.rope_kv_append(self.qkv, H, Hkv, D, self.cos, self.sin, position_ids, storage_ids, n,
                                self.k_cache[l], self.v_cache[l], M, state=state, n0=n0)
             ops.tree_attn(self.plan, l, n, state=state, n0=n0, kv_end=kv_end, prefix_len=prefix_len,
@@ -287,16 +323,32 @@ class LlamaRunner:
                 torch.mm(self.act[:n], ly["wd"].t(), out=self.peer.buf[1][:n])
                 self.peer.allreduce_add_rmsnorm(1, self.hidden, nxt, self.normed, n, self.eps)
                 continue
+            self._prefetch_join()
             self._linear(l, "o", self.attn_out, ly["wo"], self.proj, n)
+            if self.pf_budget is not None:          # window B: residual + RMSNorm; continue gate_up where window A stopped
+                wo_b = ly["wo"].numel() * 2
+                done = 0 if self.pf_budget[0] <= wo_b else \
+                    min(((self.pf_budget[0] - wo_b) // (ly["wgu"].shape[0] * 2)) // 64 * 64, ly["wgu"].shape[1])
+                self._prefetch(1, [(ly["wgu"], done)])
             self.tp.all_reduce(self.proj[:n])
             ops.add_rmsnorm(self.hidden, self.proj, ly["ln2"], self.normed, n, self.eps)
+            self._prefetch_join()
             self._linear(l, "gu", self.normed, ly["wgu"], self.gate_up, n)
+            if self.pf_budget is not None:          # window C: SiLU*up
+                self._prefetch(2, [(ly["wd"], 0)])
             ops.silu_mul(self.gate_up, self.act, n)
+            self._prefetch_join()
             self._linear(l, "d", self.act, ly["wd"], self.proj, n)
+            if self.pf_budget is not None:          # window D: residual + RMSNorm before the next layer's qkv / lm_head
+                nw = self.layers[l + 1]["wqkv"] if l + 1 < self.L else (None if skip_lm_head else self.lm_head)
+                if nw is not None:
+                    self._prefetch(3, [(nw, 0)])
             self.tp.all_reduce(self.proj[:n])
             ops.add_rmsnorm(self.hidden, self.proj, nxt, self.normed, n, self.eps)
         if skip_lm_head:                               # TP follower ranks: only rank 0 consumes logits
+            self._prefetch_join()
             return None
+        self._prefetch_join()
         m = n - logits_from
         out = logits_out if logits_out is not None else self.logits[:m]
         torch.mm(self.normed[logits_from:n], self.lm_head.t(), out=out)

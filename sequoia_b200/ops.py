@@ -158,6 +158,16 @@ def accept_greedy(target_token, succ_off, succ, depth, S, tokens, position_ids, 
           "sq_accept_greedy")
 
 
+def l2_prefetch(w: torch.Tensor, col_from: int, col_to: int):
+    """Hint: pull columns [col_from, col_to) of every row of the 2-D row-major tensor `w` into L2 (current stream)."""
+    es = w.element_size()
+    col_to = min(col_to, w.shape[1])
+    if col_to <= col_from:
+        return
+    check(_lib.load().sq_l2_prefetch(ptr(w), w.stride(0) * es, w.shape[0], col_from * es, (col_to - col_from) * es,
+                                     stream_ptr()), "sq_l2_prefetch")
+
+
 class GemmPlan:
     """C[:n] = A[:n] @ W.T for n <= 128 on the weight-streaming tcgen05 kernel (csrc/sq_gemm.cu)."""
 
