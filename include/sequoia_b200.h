@@ -38,6 +38,7 @@ extern "C" {
 #define SQ_ST_BONUS 5
 #define SQ_ST_NAN 6
 #define SQ_ST_SKIPPED 7
+#define SQ_ST_M 8 /* host-written: length of tokens / position_ids (max_length); bounds the walk's epilogue writes */
 #define SQ_ST_WORDS 16
 
 typedef uint16_t sq_half;
@@ -78,6 +79,12 @@ int sq_rope_kv_append(sq_half* qkv, int ld, int H, int Hkv, int D, const sq_half
  * k_cache / v_cache: (L, 1, Hkv, M, D). */
 int sq_kv_gather(sq_half* k_cache, sq_half* v_cache, int L, int Hkv, int M, int D, const int32_t* idx, int n,
                  int offset, const int32_t* state, int max_n, int zero_tail, void* stream);
+
+/* Same compaction for index lists too long to stage on chip (n * D * 2 B > 200 KB; reference API gather_kv with a whole
+ * accept list, Engine/Llama_KV.py:50-58): gather into the caller's scratch, then copy back.  Host-known n / offset only. */
+int64_t sq_kv_gather_scratch_bytes(int L, int Hkv, int D, int n);
+int sq_kv_gather_big(sq_half* k_cache, sq_half* v_cache, int L, int Hkv, int M, int D, const int32_t* idx, int n,
+                     int offset, void* scratch, int64_t scratch_bytes, int zero_tail, void* stream);
 
 /* ---- tree-masked attention (Llama_modules.py:127-134 draft SDPA, :220-248 target explicit attention) ---- */
 

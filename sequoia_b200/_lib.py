@@ -28,6 +28,8 @@ _SIGNATURES = {
     "sq_silu_mul": (i32, [vp, vp, i32, i32, vp]),
     "sq_rope_kv_append": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp]),
     "sq_kv_gather": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp]),
+    "sq_kv_gather_scratch_bytes": (i64, [i32, i32, i32, i32]),
+    "sq_kv_gather_big": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, i64, i32, vp]),
     "sq_attn_workspace_bytes": (i64, [i32, i32, i32, i32]),
     "sq_attn_plan_create": (i32, [C.POINTER(vp), vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, i64]),
     "sq_attn_plan_destroy": (i32, [vp]),

@@ -21,15 +21,20 @@ __device__ __forceinline__ void finish_verify(const int32_t* sh_acc, int n_new, 
                               int64_t* __restrict__ position_ids, int32_t* __restrict__ accept_idx,
                               int32_t* __restrict__ state, int max_target_seq) {
   const int a = P + n_new;
-  const bool prepare = !terminal && (a + 1 <= max_target_seq);
+  // Buffer bound (the reference raises an IndexError / shape error at the equivalent slice assignments): tokens[a] needs
+  // a < M, the re-laid tree positions need a + S - 1 < M.  M travels in the state word (set by the Tree constructor);
+  // 0 = unknown -> fall back to max_target_seq, which callers size as the buffer length.
+  const int M = state[ST_M] > 0 ? state[ST_M] : max_target_seq;
+  const bool prepare = !terminal && (a + 1 <= max_target_seq) && (a + S <= M);
+  const bool bonus_ok = !terminal && a < M;
   if (threadIdx.x == 0) {
-    if (!terminal && bonus_first) tokens[a] = bonus;        // SpecTree.py:222
+    if (bonus_ok && bonus_first) tokens[a] = bonus;         // SpecTree.py:222
     for (int j = 0; j < n_new; ++j) {                       // tokens[:a] = tokens[accept_list]  (SpecTree.py:224)
       const int src = sh_acc[j];
       accept_idx[j] = src;
       tokens[P + j] = tokens[src];
     }
-    if (!terminal && !bonus_first) tokens[a] = bonus;       // GreedyTree.py:207
+    if (bonus_ok && !bonus_first) tokens[a] = bonus;        // GreedyTree.py:207
     if (prepare) {                                          // prepare_for_next_iter (SpecTree.py:261-271)
       for (int j = 0; j < n_new; ++j) position_ids[P + j] = position_ids[sh_acc[j]];
       position_ids[a] = a;

@@ -39,7 +39,8 @@ enum StateWord : int {
   ST_P_OLD = 4,      // ground_truth_len the last verify started from
   ST_BONUS = 5,      // bonus token (-1 when terminal)
   ST_NAN = 6,        // residual had a NaN
-  ST_SKIPPED = 7,    // prepare_for_next_iter was skipped (a + 1 > max_target_seq)
+  ST_SKIPPED = 7,    // prepare_for_next_iter was skipped (a + 1 > max_target_seq, or the tree would overrun the buffers)
+  ST_M = 8,          // length of the tokens / position_ids buffers (max_length), written by the host once per prompt
   ST_WORDS = 16
 };
 

@@ -45,9 +45,50 @@ __global__ void kv_zero_tail_kernel(__half* __restrict__ k_cache, __half* __rest
     p[i] = z;
 }
 
+// Index lists too long to stage on chip (reference API: gather_kv with a whole accept list of several hundred rows):
+// gather into a global scratch (planes, n, D), then copy back -- literally the reference's temp-then-copy.
+// grid (planes, 2, chunks); dir 0: cache[idx[j]] -> scratch[j], dir 1: scratch[j] -> cache[offset + j]
+__global__ void kv_gather_scratch_kernel(__half* __restrict__ k_cache, __half* __restrict__ v_cache, int M, int D,
+                                         const int32_t* __restrict__ idx, int n, int offset, uint4* __restrict__ scratch,
+                                         int dir) {
+  __half* plane = (blockIdx.y == 0 ? k_cache : v_cache) + (int64_t)blockIdx.x * M * D;
+  const int lanes = D / 8;
+  uint4* sp = scratch + ((int64_t)blockIdx.x * 2 + blockIdx.y) * n * lanes;
+  for (int t = blockIdx.z * blockDim.x + threadIdx.x; t < n * lanes; t += gridDim.z * blockDim.x) {
+    const int j = t / lanes, c = t % lanes;
+    if (dir == 0) sp[t] = reinterpret_cast<const uint4*>(plane + (int64_t)idx[j] * D)[c];
+    else reinterpret_cast<uint4*>(plane + (int64_t)(offset + j) * D)[c] = sp[t];
+  }
+}
+
 }  // namespace sq
 
 using namespace sq;
+
+extern "C" int64_t sq_kv_gather_scratch_bytes(int L, int Hkv, int D, int n) { return (int64_t)L * Hkv * 2 * n * D * 2; }
+
+extern "C" int sq_kv_gather_big(sq_half* k_cache, sq_half* v_cache, int L, int Hkv, int M, int D, const int32_t* idx,
+                                int n, int offset, void* scratch, int64_t scratch_bytes, int zero_tail, void* stream) {
+  SQ_CHECK_ARG(D % 8 == 0 && n >= 0, "sq_kv_gather_big: bad shape");
+  SQ_CHECK_ARG(n == 0 || (scratch && scratch_bytes >= sq_kv_gather_scratch_bytes(L, Hkv, D, n)),
+               "sq_kv_gather_big: scratch too small");
+  SQ_CHECK_ARG(offset >= 0 && offset + n <= M, "sq_kv_gather_big: offset %d + n %d > M %d", offset, n, M);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int planes = L * Hkv;
+  if (n > 0) {
+    const int chunks = (n * (D / 8) + 1023) / 1024;
+    for (int dir = 0; dir < 2; ++dir) {
+      kv_gather_scratch_kernel<<<dim3(planes, 2, chunks), 256, 0, st>>>((__half*)k_cache, (__half*)v_cache, M, D, idx, n,
+                                                                       offset, (uint4*)scratch, dir);
+      SQ_CHECK_LAUNCH("sq_kv_gather_big");
+    }
+  }
+  if (zero_tail) {
+    kv_zero_tail_kernel<<<dim3(planes, 2, 4), 256, 0, st>>>((__half*)k_cache, (__half*)v_cache, M, D, n, offset, nullptr);
+    SQ_CHECK_LAUNCH("sq_kv_zero_tail");
+  }
+  return SQ_OK;
+}
 
 extern "C" int sq_kv_gather(sq_half* k_cache, sq_half* v_cache, int L, int Hkv, int M, int D, const int32_t* idx,
                             int n, int offset, const int32_t* state, int max_n, int zero_tail, void* stream) {

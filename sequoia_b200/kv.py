@@ -45,7 +45,10 @@ class KV_Cache:
         idx = torch.tensor(list(indices), dtype=torch.int32).to(self.k_cache.device, non_blocking=False) if n else None
         if n:
             assert min(indices) >= 0 and max(indices) < self.max_length
-        ops.kv_gather(self.k_cache, self.v_cache, idx, n, offset, zero_tail=zero_tail)
+        if n * self.k_cache.shape[-1] * 2 > 200 * 1024:      # too many rows to stage on chip: scratch path (any length)
+            ops.kv_gather_big(self.k_cache, self.v_cache, idx, n, offset, zero_tail=zero_tail)
+        else:
+            ops.kv_gather(self.k_cache, self.v_cache, idx, n, offset, zero_tail=zero_tail)
         self.kv_offset = offset + n
 
     # Llama_KV.py:50-58
@@ -58,7 +61,9 @@ class KV_Cache:
 
     def gather_from_state(self, accept_idx: torch.Tensor, state: torch.Tensor, max_n: int, zero_tail: bool = False):
         """Graph-static compaction: n = state[N_NEW], offset = state[P_OLD], indices = accept_idx (device int32).
-        The caller updates kv_offset once it has read the accept length back."""
+        The caller updates kv_offset once it has read the accept length back.  Unlike Llama_KV.py:65-66 the tail rows
+        (>= offset + n) are left stale here: every consumer of this path uses the packed tree mask, under which rows
+        >= kv_len are never visible (the reference-API gather_kv* methods above do zero the tail, bit-exact)."""
         ops.kv_gather(self.k_cache, self.v_cache, accept_idx, 0, 0, state=state, max_n=max_n, zero_tail=zero_tail)
 
     # Llama_KV.py:72-89 (kept for API completeness; the engine's forward appends K/V inside its RoPE kernel)

@@ -76,8 +76,8 @@ def _load_state_dict_dir(path: str) -> Dict[str, torch.Tensor]:
         for f in st:
             sd.update(load_file(os.path.join(path, f)))
         return sd
-    for f in files:
-        if f.endswith(".bin") or f.endswith(".pt"):
+    for f in files:                                    # HF shard names only (a model dir may also hold training_args.bin ...)
+        if (f.startswith("pytorch_model") and f.endswith(".bin")) or (f.startswith("model") and f.endswith(".pt")):
             sd.update(torch.load(os.path.join(path, f), map_location="cpu"))
     if not sd:
         raise FileNotFoundError(f"no weight files (*.safetensors / *.bin) in {path}")
@@ -106,6 +106,8 @@ class _DictSource:
         self.sd, self.device = sd, device
 
     def get(self, name: str, shape) -> torch.Tensor:
+        if name == "lm_head.weight" and name not in self.sd:          # tied embeddings: checkpoints omit lm_head
+            name = "model.embed_tokens.weight"
         t = self.sd[name]
         assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
         return t.to(device=self.device, dtype=F16)
@@ -138,7 +140,9 @@ def rope_cache(cfg: LlamaConfigLite, max_length: int, device):
     """LlamaRotaryEmbedding_FI (Engine/Llama_modules.py:16-45): fp32 tables, sliced [:max_length], cast to fp16."""
     d = cfg.head_dim
     inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
-    t = torch.arange(cfg.max_position_embeddings, dtype=torch.float32)
+    # the reference builds max_position_embeddings rows and slices [:max_length]; rows beyond that table would be an
+    # out-of-bounds read in the RoPE kernel, so the table always covers max_length (identical values where both exist)
+    t = torch.arange(max(cfg.max_position_embeddings, max_length), dtype=torch.float32)
     freqs = torch.outer(t, inv_freq)
     emb = torch.cat((freqs, freqs), dim=-1)
     return (emb.cos()[:max_length].to(F16).to(device).contiguous(), emb.sin()[:max_length].to(F16).to(device).contiguous())

@@ -58,6 +58,16 @@ def kv_gather(k_cache, v_cache, idx, n, offset, state=None, max_n=0, zero_tail=F
                            1 if zero_tail else 0, stream_ptr()), "sq_kv_gather")
 
 
+def kv_gather_big(k_cache, v_cache, idx, n, offset, zero_tail=False):
+    """Index lists too long for the on-chip staging of `kv_gather` (host-known n / offset): through a global scratch."""
+    lib = _lib.load()
+    L, _, Hkv, M, D = k_cache.shape
+    nbytes = lib.sq_kv_gather_scratch_bytes(L, Hkv, D, n)
+    scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=k_cache.device)
+    check(lib.sq_kv_gather_big(ptr(k_cache), ptr(v_cache), L, Hkv, M, D, ptr(idx), n, offset, ptr(scratch), nbytes,
+                               1 if zero_tail else 0, stream_ptr()), "sq_kv_gather_big")
+
+
 class AttnPlan:
     """TMA descriptors + split-KV workspace for one (qkv buffer, KV cache, output buffer) triple."""
 

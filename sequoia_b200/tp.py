@@ -6,14 +6,18 @@ sampling and the accept walk live on rank 0 only ("driver").  Every other rank (
 mirrors the driver's target-side work:
 
     driver                                   follower
-    ctrl  = [op, a, b]  --- eager bcast -->  blocks on it (the only host sync besides the driver's own per verify)
+    ctrl  = [op, a, b, mode] - eager bcast -> blocks on it (the only host sync besides the driver's own per verify)
     tokens / position_ids / state --bcast->  (inside the captured graphs on both sides)
     target forward (allreduce x 2L)  <---->  target forward shard, lm_head skipped
     accept walk
     accept_idx / state   ------ bcast --->   KV compaction of the shard
 
 The collectives are issued in the same order on every rank; in the steady state they are all inside one CUDA graph
-per rank."""
+per rank.  `mode` tells the follower HOW MANY times and how the driver executes the steady sequence for this control
+word, so both sides always issue the same number of collectives: MODE_REPLAY = one graph replay, MODE_EAGER = one eager
+execution (benchmark=True / use_graphs=False on the driver), MODE_CAPTURE = the driver is about to capture its graph
+(one eager warm-up execution + one replay; the capture pass itself executes nothing).  A follower serves ONE growmap
+(the one it was constructed with); driving a second growmap through the same followers is not supported."""
 from __future__ import annotations
 
 import torch
@@ -22,6 +26,7 @@ import torch.distributed as dist
 from .tree import _Static
 
 OP_STOP, OP_STEADY, OP_FIRST, OP_CLEAR, OP_BARRIER = 0, 1, 2, 3, 4
+MODE_REPLAY, MODE_EAGER, MODE_CAPTURE = 0, 1, 2
 
 
 class TPDriver:
@@ -32,8 +37,8 @@ class TPDriver:
         self.ctrl = torch.zeros(4, dtype=torch.int64, device=self.device)
         self.src = dist.get_global_rank(group, 0) if group is not dist.group.WORLD else 0
 
-    def send_ctrl(self, op: int, a: int = 0, b: int = 0):
-        self.ctrl.copy_(torch.tensor([op, a, b, 0], dtype=torch.int64), non_blocking=False)
+    def send_ctrl(self, op: int, a: int = 0, b: int = 0, mode: int = 0):
+        self.ctrl.copy_(torch.tensor([op, a, b, mode], dtype=torch.int64), non_blocking=False)
         dist.broadcast(self.ctrl, self.src, group=self.group)
 
     def barrier(self):
@@ -117,7 +122,7 @@ class TPFollower:
     def serve(self):
         while True:
             dist.broadcast(self.ctrl, self.src, group=self.group)
-            op, a, b, _ = self.ctrl.tolist()
+            op, a, b, mode = self.ctrl.tolist()
             if op == OP_STOP:
                 if self.device.type == "cuda":
                     torch.cuda.synchronize()
@@ -131,22 +136,30 @@ class TPFollower:
             elif op == OP_FIRST:
                 self._first(a, b)
             elif op == OP_STEADY:
-                if not self.use_graphs:
+                if mode == MODE_EAGER or not self.use_graphs:
+                    self._steady()                              # one execution on the driver, one here
+                    if mode == MODE_CAPTURE:
+                        self._steady()                          # (graphs disabled here: mirror the replay eagerly)
+                    continue
+                if mode == MODE_CAPTURE:
+                    # the driver runs a warm-up execution, a capture pass (executes nothing) and the first replay
+                    self._warm_steady()
+                    if self.graph is None:
+                        self._capture_steady()
+                elif self.graph is None:                        # driver replays a graph this rank never captured
                     self._steady()
                     continue
-                if self.graph is None:
-                    # the driver runs its warm-up pass + capture pass + first replay as three executions of the
-                    # same collective sequence; mirror them: eager (warm-up), capture (no execution), replay.
-                    self._capture_steady()
                 self.graph.replay()
 
-    def _capture_steady(self):
+    def _warm_steady(self):
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             self._steady()                      # pairs with the driver's warm-up execution
             s.synchronize()
         torch.cuda.current_stream().wait_stream(s)
+
+    def _capture_steady(self):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._steady()

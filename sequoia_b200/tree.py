@@ -377,7 +377,9 @@ class _TreeBase(Tree):
         self.depth = rt.st.depth[1:]
         st0 = torch.zeros(16, dtype=torch.int32)
         st0[0] = P
+        st0[8] = M                     # SQ_ST_M: the accept kernels bound their epilogue writes by the buffer length
         rt.state.copy_(st0)
+        self._exhausted = False
         rt.iter = 0
         # draft prefill (SpecTree.py:67-80): eager, causal rows [draft_kv_len, P)
         start = draft_kv_len
@@ -441,15 +443,25 @@ class _TreeBase(Tree):
             return n_branch_list, x1, x2
         return n_branch_list
 
+    def _check_room(self):
+        """The reference fails with an IndexError / shape error once prefix + tree no longer fit the M-long buffers
+        (SpecTree.py:222,266); the device-side walk refuses to overrun them and flags ST_SKIPPED instead, so the next
+        drafting step has nowhere to put its tree: raise here."""
+        if self._exhausted or self.ground_truth_len + self.tree_size - 1 > self.max_length:
+            raise RuntimeError(f"max_length={self.max_length} exhausted: sequence {self.ground_truth_len} + tree "
+                               f"{self.tree_size} - 1 does not fit (README.md:47: M >= tree_size + max_target_seq)")
+
     def construct_grow_map(self, benchmark=False):
         rt = self.rt
         if benchmark:
+            self._check_room()
             sample_time = compute_time = 0.0
             for i in range(self.draft_step - 1):
                 _, t1, t2 = self.collective_grow_static(None, self.grow_map["branches"][i], benchmark=True, grow_step=i)
                 sample_time += t1
                 compute_time += t2
             return sample_time, compute_time
+        self._check_room()
         if rt.external_words is not None and rt.words is not None:
             rt.words.copy_(rt.external_words[rt.iter])
         with torch.inference_mode():
@@ -474,7 +486,7 @@ class _TreeBase(Tree):
             torch.cuda.synchronize()
             t1 = time.time()
             if rt.tp is not None:
-                rt.tp.send_ctrl(1 if steady else 2, self.target_kv_len, P)
+                rt.tp.send_ctrl(1 if steady else 2, self.target_kv_len, P, mode=1)      # MODE_EAGER: one execution
             if steady:
                 rt.op_target_steady()
             else:
@@ -490,8 +502,8 @@ class _TreeBase(Tree):
             rt.op_bonus_forward()
             rt.op_publish()
         elif steady:
-            if rt.tp is not None:
-                rt.tp.send_ctrl(1)                       # OP_STEADY
+            if rt.tp is not None:                        # OP_STEADY + how this rank is about to execute it (tp.MODE_*)
+                rt.tp.send_ctrl(1, mode=1 if not rt.use_graphs else (2 if "steady" not in rt.graphs else 0))
             rt.run("steady", rt.seq_steady)
         else:
             if rt.tp is not None:
@@ -519,6 +531,9 @@ class _TreeBase(Tree):
                 self.draft_kv_len = a + 1
                 self.target_kv_len = a
                 dkv.kv_offset = a + 1
+            else:
+                self._exhausted = True
+                valid = self.tokens[:min(accept_length + 1, self.max_length)]
         else:
             valid = self.tokens[:accept_length]
         if benchmark:
