@@ -13,6 +13,11 @@ Prints ONE JSON line on rank 0 (see README / DESIGN.md for every field).  `value
 the decode loops with everything already resident in HBM; `e2e` goes through the public API from pinned HOST buffers
 (prompt H2D, Tree construction incl. its CPU-drawn random numbers, prefill, decode, D2H of the result).
 `--impl reference` times the reference's own algorithm (the torch-CPU oracle port, oracle/) on the host cores.
+`reference_gpu` (N=1) = the UNMODIFIED reference (oracle/_ref, vendored by tools/vendor_ref.py) timed on this same GPU in
+a separate process through its own tests/testbed.py setup -- the bar BASELINE.json's north_star names -- plus a
+full-size parity check of the first decode iteration of the first prompts (same weights, prompts, per-prompt seeds).
+`tp_parity` (N>1) = the tensor-parallel target checked against an unsharded copy before the timed region.
+`--config c5` = the reference's tree-shape sweep (tests/run.sh:1-30: SpecInfer policy over 30 KxL trees, M=512).
 """
 import argparse
 import json
@@ -29,7 +34,7 @@ import torch  # noqa: E402
 
 CONFIGS = {
     # name: (draft, target, growmap, greedy, T, top_p, M, prefix, max_len)
-    "c1": ("llama-68m", "llama-160m", "L40_growmaps/2-chain.pt", True, 0.6, 1.0, 256, 128, 256),
+    "c1": ("llama-68m", "llama-160m", "L40_growmaps/2-chain.pt", True, 0.6, 1.0, 288, 128, 256),
     "c2": ("llama-68m", "llama-2-7b", "A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt", False, 0.6, 1.0, 384,
            128, 256),
     # c2 with the growmap tree_search.py derives from this GPU's measured draft/verify times (B200_growmaps/)
@@ -37,6 +42,9 @@ CONFIGS = {
     "c3": ("llama-68m", "llama-2-13b", "L40_growmaps/8x8-tree.pt", False, 0.6, 1.0, 384, 128, 256),
     "c4": ("llama-2-7b", "llama-2-70b", "L40_growmaps/L40-CNN-7b-70b-stochastic.pt", False, 0.6, 1.0, 1024, 128, 256),
 }
+# tests/run.sh:1-30 of the reference: K chains of length L ("KxL-tree.pt"), driven through SpecInferTree, M=512
+SWEEP = [f"{k}x{n // k}" for n in (8, 16, 32, 64, 128) for k in (1, 2, 4, 8, 16, 32, 64, 128) if k <= n]
+CONFIGS["c5"] = ("llama-68m", "llama-2-7b", "L40_growmaps/{shape}-tree.pt", False, 0.6, 1.0, 512, 128, 256)
 METRIC = "decoded tokens/sec (mean accepted len/step in config.accepted_tokens_per_step), Sequoia tree speculative decoding, 68m->7B Llama (config c2 unless --config says otherwise)"
 
 
@@ -47,6 +55,14 @@ def load_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_tf_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f).get("bf16_tflops_sustained", 1420.0))
+    return 1420.0
 
 
 class ClockSampler:
@@ -94,6 +110,126 @@ def synthetic_prompts(n, length, seed=17):
     return sp(n, length, 32000, seed)
 
 
+def _buffers(M, dev):
+    return dict(attn_mask=torch.full((M, M), torch.finfo(torch.float16).min, dtype=torch.float16, device=dev),
+                sequence=torch.arange(M, device=dev).unsqueeze(-1), new_tokens_buffer=torch.zeros(M, device=dev).long(),
+                parents_buffer=torch.zeros(M, device=dev).long(), position_ids=torch.zeros(M, device=dev).long())
+
+
+def ref_spec(config, gm_path=None):
+    dname, tname, gmp, greedy, T, top_p, M, prefix, max_len = CONFIGS[config]
+    return dict(draft=dname, target=tname, growmap=gm_path or gmp, greedy=greedy, T=T, top_p=top_p, M=M, prefix=prefix,
+                max_len=max_len, draft_seed=1, target_seed=2)
+
+
+def run_reference_gpu(config, steps, warmup, n_parity, trace_path, timeout=900):
+    """The unmodified reference on this GPU (oracle/ref_gpu.py, separate process).  -> its JSON dict."""
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "utils.py")):
+        return {"impl": "reference_gpu", "unavailable": "oracle/_ref missing (tools/vendor_ref.py runs in the build container)"}
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_gpu.py"), "--spec", json.dumps(ref_spec(config)), "--steps",
+           str(steps), "--warmup", str(warmup), "--parity", str(n_parity), "--trace", trace_path]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, cwd=ROOT)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if not lines:
+            return {"impl": "reference_gpu", "unavailable": f"rc={r.returncode}: {r.stderr[-400:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:
+        return {"impl": "reference_gpu", "unavailable": f"{type(e).__name__}: {e}"}
+
+
+def first_iteration_trace(new_tree, draft, target, S, prefix, n_prompts):
+    """First decode iteration of the first prompts (drafted tree, accept length, accepted tokens): the records
+    oracle/ref_gpu.py saves for the reference, from this implementation."""
+    out = []
+    for pi in range(n_prompts):
+        tree = new_tree(pi)
+        tree.construct_grow_map()
+        tokens = tree.tokens[prefix:prefix + S - 1].cpu().clone()
+        valid, a, _, term = tree.verify()
+        out.append({"prompt": pi, "tree_tokens": tokens, "accept_len": int(a), "terminal": bool(term),
+                    "valid_tokens": valid[:a].cpu().clone()})
+        draft.clear_kv()
+        target.clear_kv()
+    return out
+
+
+def compare_traces(ours, ref, grow_map):
+    """Full-size parity of the first iteration: fraction of identically drafted tree nodes (a node only counts if all its
+    ancestors match too -- below a differing node the two runs legitimately sample from different draft contexts) and
+    whether the accept walk took the same path."""
+    S = grow_map["size"]
+    parent = {}
+    for p, ch in enumerate(grow_map["Successors"]):
+        for c in ch:
+            parent[c] = p
+    res = []
+    for o, r in zip(ours, ref):
+        eq = (o["tree_tokens"] == r["tree_tokens"]).tolist()
+        ok = [True] * S                                           # node 0 = root
+        for k in range(1, S):
+            ok[k] = eq[k - 1] and ok[parent[k]]
+        comparable = sum(1 for k in range(1, S) if ok[parent[k]])         # nodes whose whole ancestry matched
+        same = sum(1 for k in range(1, S) if ok[k])
+        res.append({"prompt": o["prompt"], "tree_nodes_identical": round(same / max(S - 1, 1), 4),
+                    "identical_given_same_parent": round(same / max(comparable, 1), 4),
+                    "accept_len": [o["accept_len"], r["accept_len"]],
+                    "accepted_tokens_identical": bool(o["accept_len"] == r["accept_len"] and
+                                                      torch.equal(o["valid_tokens"], r["valid_tokens"]))})
+    return res
+
+
+def tp_parity_check(dname, tname, target_tp, grow_map, cls, M, T, top_p, prefix, dev, tp_group, iters=4):
+    """Rank 0, before the timed region: the tensor-parallel target against an UNSHARDED copy of the same model on this
+    GPU -- two trees in lock-step on the same prompt, seeds and bonus-token noise."""
+    from sequoia_b200.engine import GraphInferenceEngine, GraphInferenceEngineTG
+    from sequoia_b200.tp import attach_tp
+    V = 32000
+    target_1 = GraphInferenceEngineTG(M, f"random-init:{tname}:2", device=dev)
+    drafts = [GraphInferenceEngine(M, f"random-init:{dname}:1", device=dev) for _ in range(2)]
+    attach_tp(drafts[0], target_tp, tp_group)
+    prompt = synthetic_prompts(1, prefix)[0].to(dev)
+    noise = torch.empty(iters, V, dtype=torch.float16).exponential_(1.0, generator=torch.Generator().manual_seed(5)).to(dev)
+    trees = []
+    for d, t in ((drafts[0], target_tp), (drafts[1], target_1)):
+        torch.manual_seed(4242)
+        tr = cls(prefix=prompt, device=dev, temperature=T, top_p=top_p, draft_model_engine=d, target_model_engine=t,
+                 max_length=M, max_target_seq=M, grow_map=grow_map, **_buffers(M, dev))
+        if hasattr(tr.rt, "external_noise"):
+            tr.rt.external_noise = noise
+        trees.append(tr)
+    max_rel, same_steps, forked = 0.0, 0, False
+    for it in range(iters):
+        outs = []
+        for tr in trees:
+            tr.construct_grow_map()
+            v, a, _, term = tr.verify()
+            outs.append((v.clone(), a, term, tr.rt.target_logits.float().clone()))
+        (v0, a0, t0, l0), (v1, a1, t1, l1) = outs
+        if not forked:                      # after a fork the two trees hold different tokens: logits no longer comparable
+            max_rel = max(max_rel, ((l0 - l1).abs().max() / l1.abs().max()).item())
+        if a0 == a1 and t0 == t1 and torch.equal(v0, v1) and not forked:
+            same_steps += 1
+        else:
+            forked = True
+        if t0 or t1:
+            break
+    for tr in trees:
+        tr.rt.external_noise = None
+    peer = target_tp.engine.runner.peer
+    out = {"model": tname, "iters": iters, "max_rel_logit_err": round(max_rel, 6), "accept_seq_identical_steps": same_steps,
+           "peer_error": int(peer.error()) if peer is not None else 0,
+           "attn_error": int(target_tp.engine.runner.plan.error()),
+           "how": "TP target vs an unsharded copy on rank 0, same prompt / seeds / bonus noise, lock-step; logit error "
+                  "relative to max |logit| while the two token sequences are still identical"}
+    drafts[0].clear_kv(); drafts[1].clear_kv(); target_1.clear_kv(); target_tp.clear_kv()
+    from sequoia_b200.tree import clear_runtimes
+    clear_runtimes()
+    del trees, target_1, drafts
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     from sequoia_b200 import _lib
@@ -118,15 +254,52 @@ def run_b200(args):
             os.close(null_fd)
             os.close(saved_fd)
         tp_group = dist.group.WORLD
+    if args.config == "c5":
+        assert world == 1, "the tree-shape sweep is a single-GPU configuration"
+        return run_sweep(args, dev)
     dname, tname, gm_path, greedy, T, top_p, M, prefix, max_len = CONFIGS[args.config]
     grow_map = torch.load(os.path.join(ROOT, gm_path))
     S = grow_map["size"]
-    torch.manual_seed(17)
     from sequoia_b200.engine import GraphInferenceEngine, GraphInferenceEngineTG
-    from sequoia_b200.tp import TPFollower, attach_tp
+    from sequoia_b200.model import NAMED_CONFIGS
+    from sequoia_b200.tp import TPFollower, attach_tp, stop_followers
     from sequoia_b200.tree import GreedyTree, SpecTree
+    cls = GreedyTree if greedy else SpecTree
+
+    def finish(rc=0):
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            os._exit(rc)                     # NCCL communicators captured in CUDA graphs: skip the slow teardown
+        if rc:
+            sys.exit(rc)
+
+    # ---- reference GPU arm first (N=1 only; the reference has no multi-GPU path): nothing of ours is resident yet ---------
+    ref_gpu = None
+    trace_path = os.path.join(ROOT, "gpurun_out", f"ref_gpu_trace_{args.config}.pt")
+    n_parity = 0 if args.no_reference_gpu else 4
+    if world == 1 and not args.no_reference_gpu:
+        ref_gpu = run_reference_gpu(args.config, min(args.steps, 40), 3, n_parity, trace_path)
+
+    # ---- TP parity on a model that fits unsharded next to a shard (70B: its first 8 layers' worth) ------------------------
+    tp_parity = None
+    wb = lambda c: 2 * (c.num_hidden_layers * (2 * c.hidden_size * (c.num_attention_heads + c.num_key_value_heads) * c.head_dim
+                                              + 3 * c.hidden_size * c.intermediate_size) + 2 * c.vocab_size * c.hidden_size)
+    fits = wb(NAMED_CONFIGS[tname]) * (1 + 1 / world) + 2 * wb(NAMED_CONFIGS[dname]) < 150e9
+    parity_name = tname if fits else tname + "-8l"
+    if world > 1 and not args.no_tp_parity and parity_name != tname:
+        small = GraphInferenceEngineTG(M, f"random-init:{parity_name}:2", device=dev, tp_group=tp_group)
+        if rank != 0:
+            TPFollower(small, grow_map, greedy, M, dev, tp_group).serve()
+        else:
+            tp_parity = tp_parity_check(dname, parity_name, small, grow_map, cls, M, T, top_p, prefix, dev, tp_group)
+            stop_followers(tp_group, dev)
+        del small
+        torch.cuda.empty_cache()
+        dist.barrier()
+
+    torch.manual_seed(17)
     target = GraphInferenceEngineTG(M, f"random-init:{tname}:2", device=dev, tp_group=tp_group)
-    n_prompts_max = 4096
     prompts = synthetic_prompts(64, prefix)
 
     def barrier():
@@ -134,26 +307,24 @@ def run_b200(args):
             target._tp_driver.barrier()      # follower ranks are slaved to rank 0: sync + barrier through the control op
         torch.cuda.synchronize()
 
-    def finish():
-        sys.stdout.flush()
-        sys.stderr.flush()
-        if world > 1:
-            os._exit(0)                      # NCCL communicators captured in CUDA graphs: skip the slow teardown
-
     if rank != 0:
         # follower ranks: target shard only, driven by rank 0's broadcasts
         TPFollower(target, grow_map, greedy, M, dev, tp_group).serve()
         finish()
         return
+    if world > 1 and not args.no_tp_parity and parity_name == tname:
+        tp_parity = tp_parity_check(dname, tname, target, grow_map, cls, M, T, top_p, prefix, dev, tp_group)
+    if tp_parity is not None and (tp_parity["peer_error"] or tp_parity["attn_error"]):
+        print(json.dumps({"error": "tp_parity: device-side handshake / watchdog error", "tp_parity": tp_parity}))
+        stop_followers(tp_group, dev)
+        finish(3)
     draft = GraphInferenceEngine(M, f"random-init:{dname}:1", device=dev)
     if world > 1:
         attach_tp(draft, target, tp_group)
-    buf = dict(attn_mask=torch.full((M, M), torch.finfo(torch.float16).min, dtype=torch.float16, device=dev),
-               sequence=torch.arange(M, device=dev).unsqueeze(-1), new_tokens_buffer=torch.zeros(M, device=dev).long(),
-               parents_buffer=torch.zeros(M, device=dev).long(), position_ids=torch.zeros(M, device=dev).long())
-    cls = GreedyTree if greedy else SpecTree
+    buf = _buffers(M, dev)
 
-    def new_tree(prompt_dev):
+    def new_tree(prompt_dev, pi=0):
+        torch.manual_seed(1000 + pi)         # per-prompt CPU stream for r / rand: the reference-GPU arm seeds identically
         return cls(prefix=prompt_dev, device=dev, temperature=T, top_p=top_p, draft_kv_len=0, target_kv_len=0,
                    draft_model_engine=draft, target_model_engine=target, max_length=M, max_target_seq=M,
                    grow_map=grow_map, **buf)
@@ -179,7 +350,7 @@ def run_b200(args):
                 p = pinned_prompts[(self.pi - 1) % len(prompts)].to(dev, non_blocking=True)
             else:
                 p = p.to(dev)
-            self.tree = new_tree(p)
+            self.tree = new_tree(p, self.pi - 1)
             self.len = prefix
             self.terminate = False
 
@@ -210,6 +381,13 @@ def run_b200(args):
                 e1.synchronize()
                 ms += e0.elapsed_time(e1)
             return tokens, ms
+
+    # ---- full-size parity against the reference-GPU trace (first iteration of the first prompts; untimed) --------------
+    parity = None
+    if ref_gpu is not None and "unavailable" not in ref_gpu and os.path.exists(trace_path):
+        ours = first_iteration_trace(lambda pi: new_tree(prompts[pi].to(dev), pi), draft, target, S, prefix, n_parity)
+        parity = compare_traces(ours, torch.load(trace_path), grow_map)
+        ref_gpu["first_iteration_parity"] = parity
 
     loop = Loop()
     # warm-up: captures the graphs (first prompt) and W untimed steps
@@ -244,6 +422,9 @@ def run_b200(args):
     e2e = {"value": tok2 / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": loop2.h2d // args.steps,
            "d2h_bytes_per_step": loop2.d2h // args.steps,
            "note": "includes per-prompt Tree construction (CPU-drawn r/rand as in the reference), prefill, decode"}
+    peer = target.engine.runner.peer
+    dev_err = {"peer_error": int(peer.error()) if peer is not None else 0,
+               "attn_error": int(target.engine.runner.plan.error()) | int(draft.engine.runner.plan.error())}
 
     # ---- roofline of the verify tree-attention kernel, measured live (CUDA events on the launching stream) ----------
     roof = extra = None
@@ -253,7 +434,6 @@ def run_b200(args):
     draft.clear_kv()
     target.clear_kv()
     if world > 1:
-        from sequoia_b200.tp import stop_followers
         stop_followers(tp_group, dev)
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
@@ -264,12 +444,81 @@ def run_b200(args):
                    "accepted_tokens_per_step": round(acc_per_step, 4), "parallelism": f"target tp{world}, draft on rank 0",
                    "l2": "inputs larger than L2: each step streams the target's %.1f GB of weights" % (target.engine.runner.weight_bytes() / 1e9)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": extra,
-        "wall_s_timed_region": round(wall, 3),
+        "wall_s_timed_region": round(wall, 3), "device_errors": dev_err,
     }
+    if tp_parity is not None:
+        out["tp_parity"] = tp_parity
+    if ref_gpu is not None:
+        out["reference_gpu"] = ref_gpu
+        if "value" in ref_gpu and ref_gpu["value"]:
+            out["reference_gpu"]["speedup_vs_reference_gpu"] = round(value / ref_gpu["value"], 3)
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_reference(args.config, max_seconds=25.0, max_iters=3)
     print(json.dumps(out))
-    finish()
+    finish(3 if (dev_err["peer_error"] or dev_err["attn_error"]) else 0)
+
+
+def run_sweep(args, dev):
+    """Config c5: tests/run.sh:1-30 of the reference -- tokens/s vs tree shape, SpecInfer policy, 68m -> 7B, M=512."""
+    from sequoia_b200.engine import GraphInferenceEngine, GraphInferenceEngineTG
+    from sequoia_b200.tree import SpecInferTree, clear_runtimes
+    dname, tname, gm_tmpl, _, T, top_p, M, prefix, max_len = CONFIGS["c5"]
+    target = GraphInferenceEngineTG(M, f"random-init:{tname}:2", device=dev)
+    draft = GraphInferenceEngine(M, f"random-init:{dname}:1", device=dev)
+    prompts = synthetic_prompts(64, prefix)
+    buf = _buffers(M, dev)
+    rows = []
+    sampler = ClockSampler(int(dev.split(":")[1]))
+    sampler.start()
+    total_ms = total_tokens = total_steps = launches = 0
+    steps = max(4, min(args.steps, 40))
+    for shape in SWEEP:
+        grow_map = torch.load(os.path.join(ROOT, gm_tmpl.format(shape=shape)))
+        pi, done, tokens, ms = 0, 0, 0, 0.0
+        warm = 3
+        tree = None
+        while done < steps + warm:
+            torch.manual_seed(1000 + pi)
+            if tree is not None:
+                draft.clear_kv(); target.clear_kv()
+            tree = SpecInferTree(prefix=prompts[pi % 64].to(dev), device=dev, temperature=T, top_p=top_p,
+                                 draft_model_engine=draft, target_model_engine=target, max_length=M, max_target_seq=M,
+                                 grow_map=grow_map, **buf)
+            pi += 1
+            length, term = prefix, False
+            while done < steps + warm and length < max_len and not term:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                tree.construct_grow_map()
+                valid, _, _, term = tree.verify()
+                e1.record()
+                e1.synchronize()
+                if done >= warm:
+                    ms += e0.elapsed_time(e1)
+                    tokens += valid.shape[0] - length
+                length = valid.shape[0]
+                term = term or int(tree.rt.host_state[5]) in (0, 2)
+                done += 1
+        launches += tree.rt.kernel_launches()
+        rows.append({"tree": shape, "size": int(grow_map["size"]), "levels": len(grow_map["roots"]),
+                     "tokens_per_s": round(tokens / (ms / 1e3), 1), "ms_per_step": round(ms / steps, 3),
+                     "accepted_tokens_per_step": round(tokens / steps, 3)})
+        total_ms += ms; total_tokens += tokens; total_steps += steps
+        draft.clear_kv(); target.clear_kv()
+        clear_runtimes()
+        torch.cuda.empty_cache()
+    clocks = sampler.stop()
+    best = max(rows, key=lambda r: r["tokens_per_s"])
+    out = {"metric": METRIC, "value": best["tokens_per_s"], "unit": "tokens/s", "n_gpus": 1, "steps": steps, "warmup": 3,
+           "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f16", "data": "synthetic (random-init weights, random prompts)",
+           "config": {"workload": f"c5: {dname}->{tname}, tree-shape sweep tests/run.sh:1-30 ({len(SWEEP)} KxL trees, SpecInfer "
+                                  f"policy, T={T} P={top_p} M={M}); value = best shape ({best['tree']})",
+                      "accepted_tokens_per_step": best["accepted_tokens_per_step"], "parallelism": "target tp1",
+                      "l2": "inputs larger than L2: each step streams the target's 13.5 GB of weights"},
+           "clocks": clocks, "gpu_launches": int(launches), "sweep": rows,
+           "sweep_mean_tokens_per_s": round(total_tokens / (total_ms / 1e3), 1)}
+    print(json.dumps(out))
 
 
 def _timeit(fn, iters=20, warm=3, reps=5):
@@ -297,14 +546,22 @@ def _timeit(fn, iters=20, warm=3, reps=5):
     return e0.elapsed_time(e1) / (iters * reps) * 1e3   # us
 
 
+def _sha16(path):
+    import hashlib
+    with open(path, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()[:16]
+
+
 def attention_roofline(target, grow_map, prefix, M):
-    """Verify attention (Engine/Llama_modules.py:220-248) of the steady-state shape: q = S tree rows, kv = P-1+S with
-    P = (prefix + max_len)/2-ish mid-decode value; cycles through all layers so K/V come from HBM (cache >> L2 at 7B)."""
+    """Verify attention (Engine/Llama_modules.py:220-248) of the steady-state shape: q = S tree rows, kv = P-1+S with the
+    mid-decode P (193 for prefix 128 -> 256 tokens: kv = 320 for config 2 as in SURVEY.md 8d); cycles through all layers
+    so K/V come from HBM (cache >> L2 at 7B).  HBM-bound when the arithmetic intensity is below the measured ridge
+    (configs 2/3), tensor-pipe-bound otherwise (config 4's GQA shape)."""
     from sequoia_b200 import ops
     from sequoia_b200.tree import pack_tree_mask
     rn = target.engine.runner
     S = grow_map["size"]
-    P = 193                                    # kv = 320 as in SURVEY.md 8(d) for config 2
+    P = min(193, M - S + 1)
     kv = P - 1 + S
     bits = pack_tree_mask(grow_map["mask"]).to(rn.device)
     state = torch.zeros(16, dtype=torch.int32, device=rn.device)
@@ -324,17 +581,29 @@ def attention_roofline(target, grow_map, prefix, M):
     alg_bytes = 2 * D * 2 * (rn.Hkv * kv + rn.H * S)           # K+V read once, Q read + O write
     flops = 4 * rn.H * S * kv * D
     peak, how = load_peaks()
+    tf_peak = load_tf_peak()
+    # measured DRAM traffic: only if the committed ncu capture is of THIS kernel source and THIS shape
     traffic = None
     tp = os.path.join(ROOT, "profiles", "attn_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            t = json.load(f)
+        if t.get("kernel_sha16") == _sha16(os.path.join(ROOT, "sequoia_b200", "csrc", "sq_attn.cu")) and \
+                t.get("shape") == [rn.H, rn.Hkv, S, kv, D]:
+            traffic = t.get("dram_bytes_per_launch")
     rn.k_cache.zero_()
     rn.v_cache.zero_()
-    return {"kernel": "tree_attn_tc_kernel<128,false> (verify attention incl. its in-cluster split-KV reduction, q=%d kv=%d H=%d)" % (S, kv, rn.H),
-            "bound": "hbm", "achieved": round(alg_bytes / (us * 1e-6) / 1e9, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(alg_bytes / (us * 1e-6) / 1e9 / peak, 4), "traffic": traffic, "peak_source": how,
-            "algorithmic_bytes": alg_bytes, "us_per_launch": round(us, 3), "tflops": round(flops / (us * 1e-6) / 1e12, 2)}
+    gbs, tfs = alg_bytes / (us * 1e-6) / 1e9, flops / (us * 1e-6) / 1e12
+    tensor_bound = flops / alg_bytes > tf_peak * 1e12 / (peak * 1e9)
+    out = {"kernel": "tree_attn_tc_kernel<%d> (verify attention, whole launch incl. split-KV reduction; H=%d Hkv=%d q=%d kv=%d)"
+                     % (D, rn.H, rn.Hkv, S, kv),
+           "bound": "tensor" if tensor_bound else "hbm",
+           "achieved": round(tfs if tensor_bound else gbs, 2), "peak": tf_peak if tensor_bound else peak,
+           "unit": "TFLOP/s" if tensor_bound else "GB/s",
+           "frac": round((tfs / tf_peak) if tensor_bound else (gbs / peak), 4), "traffic": traffic, "peak_source": how,
+           "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops, "us_per_launch": round(us, 3),
+           "GBps": round(gbs, 1), "tflops": round(tfs, 2)}
+    return out
 
 
 def micro_kernels(draft, target, tree, grow_map):
@@ -365,6 +634,33 @@ def micro_kernels(draft, target, tree, grow_map):
     rn = target.engine.runner
     us = _timeit(lambda: ops.add_rmsnorm(rn.hidden, rn.proj, rn.norm, rn.normed, S, rn.eps))
     out["add_rmsnorm(S rows)"] = {"us": round(us, 2), "GBps": round(S * rn.h * 2 * 4 / us / 1e3, 1)}
+    st2 = torch.zeros(16, dtype=torch.int32, device=rt.device)
+    st2[0] = 150
+    us = _timeit(lambda: ops.rope_kv_append(rn.qkv, rn.H, rn.Hkv, rn.D, rn.cos, rn.sin, rt.position_ids, rt.storage_ids, S,
+                                            rn.k_cache[0], rn.v_cache[0], rn.M, state=st2, n0=0))
+    b = S * (rn.H + 2 * rn.Hkv) * rn.D * 2 + S * (rn.H + 2 * rn.Hkv) * rn.D * 2      # read qkv, write q + K + V
+    out["rope_kv_append(S rows)"] = {"us": round(us, 2), "GBps": round(b / us / 1e3, 1)}
+    us = _timeit(lambda: ops.silu_mul(rn.gate_up, rn.act, S))
+    out["silu_mul(S rows)"] = {"us": round(us, 2), "GBps": round(S * rn.I * 2 * 3 / us / 1e3, 1)}
+    if rn.peer is not None and rt.tp is not None:
+        # every rank must issue the same launches (each one handshakes with its peers): followers mirror via OP_MICRO
+        from sequoia_b200.tp import OP_MICRO, micro_allreduce
+        k = 64
+        rt.tp.send_ctrl(OP_MICRO, k, S)
+        micro_allreduce(rn, k, S)                        # warm-up round
+        torch.cuda.synchronize()
+        rt.tp.send_ctrl(OP_MICRO, k, S)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        micro_allreduce(rn, k, S)
+        e1.record()
+        e1.synchronize()
+        us = e0.elapsed_time(e1) / k * 1e3
+        N = rn.tp.size
+        out["tp_allreduce_add_rmsnorm(S rows)"] = {"us": round(us, 2), "ranks": N,
+                                                   "nvlink_rx_GBps": round((N - 1) * S * rn.h * 2 / us / 1e3, 1),
+                                                   "note": "eager back-to-back launches incl. host launch gaps"}
+    rn.k_cache[0].zero_(); rn.v_cache[0].zero_()
     return out
 
 
@@ -406,10 +702,21 @@ def cpu_reference(config, max_seconds, max_iters, warm_iters=1):
     torch.set_num_threads(ncores)
     grow_map = torch.load(os.path.join(ROOT, gm_path))
 
-    def shared_weights(name, seed):
+    def weights(name, seed):
+        """The SAME random-init model the GPU arms use: drawn by sequoia_b200.model._RandomInit's seeded CUDA generator
+        (tensor by tensor, copied to host).  Without a CUDA device (build container) fall back to the oracle's own CPU
+        init with one layer's tensors aliased across layers (bounded init time) and say so."""
         c = NAMED_CONFIGS[name]
         cfg = O.LlamaCfg(c.hidden_size, c.intermediate_size, c.num_hidden_layers, c.num_attention_heads,
                          c.num_key_value_heads, c.vocab_size, c.rms_norm_eps, c.rope_theta, c.max_position_embeddings)
+        if torch.cuda.is_available():
+            from sequoia_b200.model import _RandomInit, full_state_dict
+            gen = _RandomInit(c, seed, torch.device("cuda:0"))
+
+            class ToHost:
+                def get(self, n, shape):
+                    return gen.get(n, shape).cpu()
+            return cfg, full_state_dict(c, ToHost()), True
         one = O.LlamaCfg(c.hidden_size, c.intermediate_size, 1, c.num_attention_heads, c.num_key_value_heads,
                          c.vocab_size, c.rms_norm_eps, c.rope_theta, c.max_position_embeddings)
         w1 = O.init_llama_weights(one, seed)
@@ -418,14 +725,14 @@ def cpu_reference(config, max_seconds, max_iters, warm_iters=1):
             for k, v in w1.items():
                 if k.startswith("model.layers.0."):
                     w[k.replace("model.layers.0.", f"model.layers.{l}.")] = v
-        return cfg, w
+        return cfg, w, False
 
     t0 = time.time()
-    dcfg, dw = shared_weights(dname, 1)
-    tcfg, tw = shared_weights(tname, 2)
+    dcfg, dw, same_d = weights(dname, 1)
+    tcfg, tw, same_t = weights(tname, 2)
     draft = O.EngineOracle(O.LlamaOracle(dcfg, dw, M, "FI"))
     target = O.EngineOracle(O.LlamaOracle(tcfg, tw, M, "TG"))
-    torch.manual_seed(17)
+    torch.manual_seed(1000)                          # prompt 0's seed in the GPU arms
     prompt = synthetic_prompts(1, prefix)[0]
     tree = (O.GreedyTreeOracle(draft, target, prompt, grow_map, max_length=M) if greedy else
             O.SpecTreeOracle(draft, target, prompt, grow_map, temperature=T, top_p=top_p, max_length=M))
@@ -447,9 +754,11 @@ def cpu_reference(config, max_seconds, max_iters, warm_iters=1):
     return {"value": round(tokens / dt, 4) if dt > 0 and iters else None, "unit": "tokens/s", "cores": ncores,
             "kind": "port", "ms_per_step": round(dt / max(iters, 1) * 1e3, 1), "steps_timed": iters,
             "accepted_tokens_per_step": round(tokens / max(iters, 1), 3),
+            "same_weights_as_gpu_arm": bool(same_d and same_t),
             "sample": f"{iters} steady decode iteration(s) of the torch-CPU oracle (fp16, {ncores} threads) on the same "
-                      f"shapes/growmap after 1 untimed prefill iteration; target layers alias one layer's weights "
-                      f"(init {init_s:.0f}s)"}
+                      f"shapes/growmap/prompt after 1 untimed prefill iteration; "
+                      + ("same random-init weights as the GPU arm" if same_d and same_t else
+                         "no CUDA device: target layers alias one layer's CPU-drawn weights") + f" (init {init_s:.0f}s)"}
 
 
 def run_reference(args):
@@ -480,6 +789,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=list(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-micro", action="store_true", help="skip the per-kernel micro timings (for ncu launch lists)")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-on-this-GPU arm (N=1)")
+    ap.add_argument("--no-tp-parity", action="store_true", help="skip the TP-vs-unsharded parity check (N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

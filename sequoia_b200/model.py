@@ -51,6 +51,9 @@ NAMED_CONFIGS = {
     "llama-2-7b": LlamaConfigLite(4096, 11008, 32, 32, 32, rms_norm_eps=1e-5, max_position_embeddings=4096),
     "llama-2-13b": LlamaConfigLite(5120, 13824, 40, 40, 40, rms_norm_eps=1e-5, max_position_embeddings=4096),
     "llama-2-70b": LlamaConfigLite(8192, 28672, 80, 64, 8, rms_norm_eps=1e-5, max_position_embeddings=4096),
+    # the first 8 layers' worth of a 70B-shaped model: TP parity checks at the real head / FFN shapes where the
+    # unsharded 138 GB model cannot sit next to a shard (bench.py tp_parity, tests/test_gpu_tp.py)
+    "llama-2-70b-8l": LlamaConfigLite(8192, 28672, 8, 64, 8, rms_norm_eps=1e-5, max_position_embeddings=4096),
 }
 
 
@@ -161,6 +164,26 @@ class TPInfo:
         if self.size > 1:
             import torch.distributed as dist
             dist.all_reduce(t, group=self.group)
+
+
+def full_state_dict(cfg: LlamaConfigLite, src) -> Dict[str, torch.Tensor]:
+    """The whole model as an HF-named state dict, tensors requested from `src` in EXACTLY the order
+    `load_sharded_weights` requests them -- so a seeded `_RandomInit` yields the same weights either way.  Used to hand
+    the very same random-init model to the reference implementation / the CPU oracle in bench.py."""
+    h, D, V = cfg.hidden_size, cfg.head_dim, cfg.vocab_size
+    Hf, Hkvf, If = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.intermediate_size
+    sd = {"model.embed_tokens.weight": src.get("model.embed_tokens.weight", (V, h))}
+    for l in range(cfg.num_hidden_layers):
+        p = f"model.layers.{l}."
+        for name, shape in (("self_attn.q_proj.weight", (Hf * D, h)), ("self_attn.k_proj.weight", (Hkvf * D, h)),
+                            ("self_attn.v_proj.weight", (Hkvf * D, h)), ("self_attn.o_proj.weight", (h, Hf * D)),
+                            ("mlp.gate_proj.weight", (If, h)), ("mlp.up_proj.weight", (If, h)),
+                            ("mlp.down_proj.weight", (h, If)), ("input_layernorm.weight", (h,)),
+                            ("post_attention_layernorm.weight", (h,))):
+            sd[p + name] = src.get(p + name, shape)
+    sd["model.norm.weight"] = src.get("model.norm.weight", (h,))
+    sd["lm_head.weight"] = src.get("lm_head.weight", (V, h))
+    return sd
 
 
 def load_sharded_weights(cfg: LlamaConfigLite, src, rank: int, tp: int) -> dict:

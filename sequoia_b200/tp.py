@@ -25,7 +25,7 @@ import torch.distributed as dist
 
 from .tree import _Static
 
-OP_STOP, OP_STEADY, OP_FIRST, OP_CLEAR, OP_BARRIER = 0, 1, 2, 3, 4
+OP_STOP, OP_STEADY, OP_FIRST, OP_CLEAR, OP_BARRIER, OP_MICRO = 0, 1, 2, 3, 4, 5
 MODE_REPLAY, MODE_EAGER, MODE_CAPTURE = 0, 1, 2
 
 
@@ -69,6 +69,13 @@ def stop_followers(group, device):
     d.send_ctrl(OP_STOP)
     if torch.device(device).type == "cuda":
         torch.cuda.synchronize()
+
+
+def micro_allreduce(runner, k: int, n: int):
+    """k back-to-back fused all-reduce + residual + RMSNorm launches of n rows on this rank (every rank must issue the
+    same k: each launch handshakes with its peers).  Used by bench.py to time the kernel on the device."""
+    for i in range(k):
+        runner.peer.allreduce_add_rmsnorm(i & 1, runner.hidden, runner.norm, runner.normed, n, runner.eps)
 
 
 class TPFollower:
@@ -133,6 +140,8 @@ class TPFollower:
                 dist.barrier(group=self.group)
             elif op == OP_CLEAR:
                 self.target.clear_kv()
+            elif op == OP_MICRO:                                # bench.py: `a` fused all-reduce launches of `b` rows
+                micro_allreduce(self.target.engine.runner, int(a), int(b))
             elif op == OP_FIRST:
                 self._first(a, b)
             elif op == OP_STEADY:

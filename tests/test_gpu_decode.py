@@ -21,9 +21,12 @@ DEC = torch.load(os.path.join(G, "decode_golden.pt"))
 DEV = "cuda:0"
 F16 = torch.float16
 REL_TOL = 4e-3          # of the row's logit range: fp16 GEMM-order noise through the tiny models
-# trees with hundreds of sampled nodes per iteration hit an fp16 score (near-)tie almost surely:
-# for these an EXPLAINED fork in the very first iteration is accepted, provided most of the tree was drafted identically
-BIG_TREES = {"spec_a100_128": 0.25, "spec_l40_768": 0.05}
+# trees with hundreds of sampled nodes per iteration hit an fp16 score (near-)tie almost surely: the
+# plain lock-step below stops at such a fork, so the BASELINE-sized trees are additionally run TEACHER-FORCED
+# (test_decode_teacher_forced): every level / iteration is compared, and >= MIN_IDENTICAL of all drafted nodes must match
+BIG_TREES = ("spec_a100_128", "spec_l40_768")
+MIN_IDENTICAL = 0.95
+DRAFT_LOGIT_TOL = 2e-3  # GPU vs CPU-oracle draft / target logits of the SAME token tree, relative to the row's max |logit|
 
 
 def _engines(dkey, tkey, M):
@@ -134,10 +137,8 @@ def _lockstep(name, graphs, check_golden):
             if not torch.equal(got, otree.tokens[P:P + S - 1]):
                 ok, why = _explained_tree_mismatch(otree, got, P, gm, mode)
                 assert ok, f"{name} iter {it}: drafted tree differs and is NOT a near-tie ({why})"
-                same = float((got == otree.tokens[P:P + S - 1]).float().mean())
                 if name in BIG_TREES and it == 0:
-                    assert same >= BIG_TREES[name], f"{name}: only {same:.2f} of the first tree matches"
-                    matched = max(matched, 1)
+                    matched = max(matched, 1)        # (the teacher-forced test below carries the quantitative bar)
                 print(f"{name} iter {it}: fork on a near-tie ({why}); {matched} iterations matched exactly")
                 break
             ov, oa, _, oterm = otree.verify()
@@ -233,3 +234,152 @@ def test_reference_api_graph_inference_matches_inference():
     eng.clear_kv()
     b = eng.inference(ids, sto, pos, mask)
     assert a.shape == (1, 4, cases.V) and torch.equal(a, b)
+
+
+# ---- teacher-forced lock-step: every level of every iteration is compared, forks are repaired and counted -------------
+def _walk_spec(p_rows, draft_logits, tokens, r, succ, P, T):
+    """Tree/SpecTree.py:137-157,203-213 on explicit tensors (fp16 CPU): -> accepted absolute slots (without the prefix)."""
+    from torch.nn.functional import softmax
+    acc, parent = [], P - 1
+    dl = draft_logits.clone()
+    while True:
+        node = parent - (P - 1)
+        p, row, nxt = p_rows[node], dl[node], -1
+        for c in succ[node]:
+            tok = tokens[c + (P - 1)]
+            q = softmax(row / T, dim=-1)
+            if p[tok] > r[c + (P - 1)] * q[tok]:
+                nxt = c + (P - 1)
+                break
+            p = O.get_residual(p, q)
+            row[tok] = torch.finfo(F16).min
+        if nxt < 0:
+            return acc
+        acc.append(nxt)
+        if int(tokens[nxt]) in (0, 2):
+            return acc
+        parent = nxt
+
+
+def _teacher_forced(name, table):
+    """Oracle and GPU tree side by side, the GPU run level by level (eager ops).  After each sampling step the GPU's new
+    tokens are compared with the oracle's; a difference must be reproduced EXACTLY by the oracle's sampling function fed
+    the GPU's own draft logits (i.e. it is attributable to the bounded logit noise, not to the sampler), is counted, and
+    the GPU tokens are overwritten with the oracle's so that every later level / iteration stays comparable.  An accept
+    fork is handled the same way (the walk replayed on the GPU's own logits must give the GPU's accept list), after which
+    the GPU state is rebuilt from the oracle's sequence.  -> (identical nodes, drafted nodes, accept forks, iterations)"""
+    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = table[name]
+    assert mode in ("spec", "greedy")
+    gm = cases.load_growmap(gm_name)
+    S, T = gm["size"], 0.6
+    prompt = cases.make_prompt(pseed, plen)
+    dcfg, dw = cases.model_weights(dkey)
+    tcfg, tw = cases.model_weights(tkey)
+    od, ot = O.EngineOracle(O.LlamaOracle(dcfg, dw, M, "FI")), O.EngineOracle(O.LlamaOracle(tcfg, tw, M, "TG"))
+    noise = torch.empty(iters, cases.V, dtype=F16).exponential_(1.0, generator=torch.Generator().manual_seed(5))
+    torch.manual_seed(rng_seed)
+    otree = (O.SpecTreeOracle(od, ot, prompt, gm, temperature=T, top_p=1.0, max_length=M, bonus_noise=noise)
+             if mode == "spec" else O.GreedyTreeOracle(od, ot, prompt, gm, max_length=M))
+    draft, target = _engines(dkey, tkey, M)
+    torch.manual_seed(rng_seed)
+    tree = _make_tree(mode, draft, target, prompt, gm, M)
+    rt = tree.rt
+    rt.use_graphs = False
+    rt.external_noise = noise.to(DEV) if mode == "spec" else None
+    same = total = forks = done = 0
+    worst_logit = 0.0
+    try:
+        for it in range(iters):
+            P = tree.ground_truth_len
+            assert P == otree.ground_truth_len
+            for i in range(rt.st.draft_step - 1):
+                lv = rt.st.levels[i]
+                n0, tb, k = lv["n0"], lv["tb"], lv["k"]
+                parents = torch.tensor(gm["roots"][i], dtype=torch.long)
+                # draft logits of this level's parents: same token tree on both sides (teacher forcing) => comparable
+                gl = tree.draft_logits[parents.to(DEV)].cpu()
+                ol = otree.draft_logits[parents]
+                worst_logit = max(worst_logit, float(((gl.float() - ol.float()).abs().amax(-1) / ol.float().abs().amax(-1)).max()))
+                otree.collective_grow_static(otree.roots[i], gm["branches"][i], i)
+                rt.op_sample(i)
+                lo, hi = P - 1 + n0, P - 1 + n0 + tb
+                got, ref = tree.tokens[lo:hi].cpu(), otree.tokens[lo:hi]
+                total += tb
+                same += int((got == ref).sum())
+                if not torch.equal(got, ref):
+                    # the sampler itself must be exact: oracle sampling on the GPU's logits == GPU tokens
+                    pos = (O.sampling_without_replacement(gl, otree.rand[parents], k, T) if mode == "spec"
+                           else O.sampling_argmax(gl, k))
+                    want = pos[O.sample_gather_index(gm["branches"][i])]
+                    assert torch.equal(want, got), f"{name} iter {it} level {i}: GPU sample != oracle sampler on GPU logits"
+                    tree.tokens[lo:hi] = ref.to(DEV)                 # teacher forcing
+                rt.op_draft_level(i)
+            tree.num_nodes = tree.draft_kv_len = P + S - 1
+            draft.engine.kv_cache.kv_offset = P + S - 1
+            # the oracle mutates its draft logits during the walk: snapshot what the GPU walk replay needs first
+            g_draft = tree.draft_logits[:S].cpu().clone()
+            g_tokens = tree.tokens.cpu().clone()
+            ov, oa, _, oterm = otree.verify()
+            valid, a, _, terminal = tree.verify()
+            tl_g, tl_o = rt.target_logits.float().cpu(), otree.raw_target_logits.float()
+            worst_logit = max(worst_logit, float(((tl_g - tl_o).abs().amax(-1) / tl_o.abs().amax(-1)).max()))
+            got_list, ref_list = tree.accept_list(), otree.last_trace.accept_list
+            done += 1
+            if got_list != ref_list:
+                forks += 1
+                if mode == "spec":
+                    p_rows = torch.softmax(rt.target_logits.cpu() / T, dim=-1)
+                    mine = _walk_spec(p_rows, g_draft, g_tokens, otree.r, gm["Successors"], P, T)
+                else:
+                    tt, mine, parent = rt.target_logits.cpu().argmax(-1), [], 0
+                    while True:
+                        nxt = next((c for c in gm["Successors"][parent] if int(g_tokens[P - 1 + c]) == int(tt[parent])), -1)
+                        if nxt < 0:
+                            break
+                        mine.append(P - 1 + nxt)
+                        if int(g_tokens[P - 1 + nxt]) in (0, 2):
+                            break
+                        parent = nxt
+                assert got_list[P:] == mine, f"{name} iter {it}: GPU walk {got_list[P:]} != walk replayed on GPU logits {mine}"
+                if oterm or it == iters - 1:
+                    break
+                # rebuild the GPU state from the oracle's sequence and continue
+                draft.clear_kv(); target.clear_kv()
+                tree = _make_tree(mode, draft, target, otree.tokens[:otree.ground_truth_len].clone(), gm, M)
+                rt = tree.rt
+                rt.use_graphs = False
+                if mode == "spec":
+                    rt.r[:M].copy_(otree.r); rt.rand.copy_(otree.rand)
+                rt.iter = otree.iter
+                continue
+            assert (a, terminal) == (oa, oterm) and torch.equal(valid.cpu(), ov), f"{name} iter {it}: returned tokens"
+            assert torch.equal(tree.position_ids.cpu(), otree.position_ids)
+            if terminal:
+                break
+    finally:
+        rt.external_noise = None
+        rt.use_graphs = True
+        draft.clear_kv(); target.clear_kv()
+    assert draft.engine.runner.plan.error() == 0 and target.engine.runner.plan.error() == 0
+    return same, total, forks, done, worst_logit
+
+
+@pytest.mark.parametrize("name", list(BIG_TREES) + ["spec_8x8", "greedy_4x4", "spec_same_8x8"])
+def test_decode_teacher_forced(name):
+    same, total, forks, done, worst = _teacher_forced(name, cases.DECODE_CASES)
+    frac = same / max(total, 1)
+    print(f"{name}: {same}/{total} drafted nodes identical ({frac:.4f}), {forks} accept forks in {done} iterations, "
+          f"worst logit rel err {worst:.2e}")
+    os.makedirs(os.path.join(os.path.dirname(G), "..", "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(G), "..", "gpurun_out", "teacher_forced.log"), "a") as f:
+        f.write(f"{name} identical={same}/{total} frac={frac:.4f} accept_forks={forks} iters={done} logit_rel={worst:.3e}\n")
+    assert frac >= MIN_IDENTICAL, f"{name}: only {frac:.3f} of the drafted nodes identical to the oracle"
+    assert worst <= DRAFT_LOGIT_TOL, f"{name}: GPU logits differ from the oracle's by {worst:.2e} (rel. to max |logit|)"
+    assert done == cases.DECODE_CASES[name][7] or forks > 0 or done >= 1
+
+
+@pytest.mark.parametrize("name", [n for n, c in cases.SWEEP_CASES.items() if c[1] in ("spec", "greedy")])
+def test_sweep_shapes_teacher_forced(name):
+    """tests/run.sh tree shapes (K chains of length L) on the GPU, SpecTree / GreedyTree policies."""
+    same, total, forks, done, worst = _teacher_forced(name, cases.SWEEP_CASES)
+    assert same / max(total, 1) >= MIN_IDENTICAL and worst <= DRAFT_LOGIT_TOL and done >= 1, (same, total, forks, worst)

@@ -223,6 +223,12 @@ def _attn_reference(q, kc, vc, vis, H, Hkv, D):
     (64, 4, 4, 256, 100, "L40_growmaps/8x8-tree.pt", "steady"),
     (64, 12, 12, 384, 128, "A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt", "level"),
     (128, 4, 4, 256, 77, "L40_growmaps/8x8-tree.pt", "one"),
+    # config 4 (7B -> 70B, 768-node tree, M = 1024) at the REAL head shapes: one TP-8 rank (8 q heads on 1 kv head) and
+    # the unsharded model (64 q heads on 8 kv heads), Engine/Llama_modules.py:223-224 repeat_kv 8:1
+    (128, 8, 1, 1024, 200, "L40_growmaps/L40-CNN-7b-70b-stochastic.pt", "steady"),
+    (128, 64, 8, 1024, 256, "L40_growmaps/L40-CNN-7b-70b-stochastic.pt", "steady"),
+    (128, 8, 1, 1024, 129, "L40_growmaps/L40-CNN-7b-70b-stochastic.pt", "first"),
+    (128, 32, 32, 1024, 140, "L40_growmaps/L40-CNN-7b-70b-stochastic.pt", "level"),      # config 4's 7B draft
 ])
 @pytest.mark.parametrize("impl", [1, 0])
 def test_tree_attention(D, H, Hkv, M, P, gm, mode, impl):
@@ -453,6 +459,91 @@ def test_engine_forward_logits_vs_oracle(kind, key):
         with pytest.raises(ValueError):
             eng.inference(prompt[:4].unsqueeze(0).to(DEV), sto[:4].to(DEV), pos[:4].unsqueeze(0).to(DEV),
                           win[:4, :7][None, None].to(DEV))
+
+
+def test_7b_shaped_layer_logits_within_1e3_of_fp32():
+    """north_star: logits within 1e-3 (relative).  One decoder layer at the 7B shape (h=4096, I=11008, 32 heads of 128,
+    V=32000), prefix rows then the 128-node tree rows of config 2, against the oracle run in FP32 (the same fp16 weights
+    upcast, no intermediate roundings) -- i.e. against the exact arithmetic both fp16 implementations approximate."""
+    from sequoia_b200.engine import GraphInferenceEngineTG
+    cfg = O.LlamaCfg(hidden_size=4096, intermediate_size=11008, num_hidden_layers=1, num_attention_heads=32,
+                     num_key_value_heads=32, vocab_size=cases.V, rms_norm_eps=1e-5)
+    w = O.init_llama_weights(cfg, 909)
+    gm = cases.load_growmap("A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt")
+    S, P, M = gm["size"], 64, 256
+    tot = P + S - 1
+    prompt = cases.make_prompt(78, tot)
+    win = O.window_mask(O.build_full_attn_mask(M, gm["mask"]), M, tot)
+    pos = torch.zeros(M, dtype=torch.long)
+    pos[:P] = torch.arange(P)
+    pos[P:tot] = gm["depth"][1:] + P - 1
+    sto = torch.arange(M)
+    orc = O.EngineOracle(O.LlamaOracle(cfg, {k: v.float() for k, v in w.items()}, M, "TG", dtype=torch.float32))
+    eng = GraphInferenceEngineTG(M, {"config": cfg, "state_dict": w}, device=DEV)
+    worst = 0.0
+    for (a, b, m) in ((0, P, win[:P, :P][None, None]), (P, tot, win[P:tot, :tot][None, None])):
+        ref = orc.inference(prompt[a:b].unsqueeze(0), sto[a:b], pos[a:b].unsqueeze(0), m.float())
+        got = eng.inference(prompt[a:b].unsqueeze(0).to(DEV), sto[a:b].to(DEV), pos[a:b].unsqueeze(0).to(DEV), m.to(DEV))
+        scale = ref.abs().amax(dim=-1, keepdim=True)
+        worst = max(worst, ((got.float().cpu() - ref).abs() / scale).max().item())
+    os.makedirs(os.path.join(os.path.dirname(G), "..", "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(G), "..", "gpurun_out", "logit_err.log"), "a") as f:
+        f.write(f"7B-shaped layer (h=4096 I=11008 H=32 D=128 V=32000), rows {tot}: max rel logit err vs fp32 = {worst:.3e}\n")
+    assert eng.engine.runner.plan.error() == 0
+    assert worst < 1e-3, f"logits differ from the fp32 reference by {worst:.3e} (relative to the row's max |logit|)"
+
+
+def test_accept_epilogue_respects_buffer_length():
+    """the walk's epilogue must not write tokens[a] / position_ids[a+k] beyond the M-long buffers (the
+    reference raises at the equivalent slice assignment); it flags ST_SKIPPED instead and leaves the tail untouched."""
+    sops = ops()
+    gm = cases.load_growmap("L40_growmaps/4x4-tree.pt")
+    from sequoia_b200.tree import _Static
+    st = _Static(gm, DEV)
+    S, V = st.S, cases.V
+    M = 64
+    guard = 32
+    for P in (M - S - 1, M - S + 1):                 # next tree still fits after one acceptance / would overrun the buffers
+        tokens = torch.full((M + guard,), 7, dtype=torch.int64, device=DEV)
+        pos = torch.full((M + guard,), -5, dtype=torch.int64, device=DEV)
+        tokens[:P] = torch.arange(3, 3 + P)
+        tokens[P:P + S - 1] = torch.arange(100, 100 + S - 1)            # tree tokens
+        target_token = torch.zeros(S, dtype=torch.int64, device=DEV)
+        target_token[0] = 100                                            # accept node 1, then nothing
+        target_token[1] = 31999
+        accept_idx = torch.zeros(max(S, 8), dtype=torch.int32, device=DEV)
+        state = torch.zeros(16, dtype=torch.int32, device=DEV)
+        state[0], state[8] = P, M
+        sops.accept_greedy(target_token, st.succ_off, st.succ, st.depth, S, tokens, pos, accept_idx, state, M + guard)
+        torch.cuda.synchronize()
+        hs = state.cpu()
+        a = int(hs[1])
+        assert a == P + 1
+        assert torch.all(tokens[M:] == 7) and torch.all(pos[M:] == -5), "epilogue wrote past the buffer length"
+        if a + S <= M:
+            assert int(hs[7]) == 0 and int(hs[0]) == a + 1
+        else:
+            assert int(hs[7]) == 1 and int(hs[0]) == P, "overrun must skip prepare_for_next_iter"
+
+
+def test_kv_gather_long_index_list():
+    """gather_kv with an index list too long to stage on chip (reference API: whole accept lists, Llama_KV.py:50-58)."""
+    from sequoia_b200.kv import KV_Cache
+    cfg = O.LlamaCfg(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                     num_key_value_heads=2, vocab_size=cases.V)
+    M = 2048
+    g = torch.Generator().manual_seed(3)
+    kc = torch.randn(2, 1, 2, M, 128, generator=g).to(F16)
+    vc = torch.randn(2, 1, 2, M, 128, generator=g).to(F16)
+    idx = torch.randperm(M, generator=g)[:1500].tolist()                # arbitrary order, far beyond 800 rows
+    kv = KV_Cache(cfg, max_length=M, device=DEV)
+    kv.k_cache.copy_(kc.to(DEV)); kv.v_cache.copy_(vc.to(DEV))
+    kv.gather_kv(idx)
+    ref = O.KVCacheOracle(2, 2, 128, M, F16)
+    ref.k_cache.copy_(kc); ref.v_cache.copy_(vc)
+    ref.gather_kv(idx)
+    assert kv.kv_offset == ref.kv_offset == 1500
+    assert torch.equal(kv.k_cache.cpu(), ref.k_cache) and torch.equal(kv.v_cache.cpu(), ref.v_cache)
 
 
 # ------------------------------------------------------------------------------------------------ weight-streaming GEMM

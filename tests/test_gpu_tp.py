@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, variant="tiny"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -35,18 +35,26 @@ def _worker(rank, world, port, q):
     dev = f"cuda:{rank}"
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
     grp = dist.group.WORLD
-    gm = cases.load_growmap("L40_growmaps/8x8-tree.pt")
-    M, plen, iters = 256, 100, 4
     dcfg, dw = cases.model_weights("draft")
-    tcfg, tw = cases.model_weights("target_gqa")                   # H=4, Hkv=2 -> shards of 2 q heads + 1 kv head
-    target_tp = GraphInferenceEngineTG(M, {"config": tcfg, "state_dict": tw}, device=dev, tp_group=grp)
+    if variant == "tiny":
+        gm = cases.load_growmap("L40_growmaps/8x8-tree.pt")
+        M, plen, iters = 256, 100, 4
+        tcfg, tw = cases.model_weights("target_gqa")               # H=4, Hkv=2 -> shards of 2 q heads + 1 kv head
+        tspec = {"config": tcfg, "state_dict": tw}
+    else:
+        # config 4's REAL target shapes (h=8192, I=28672, 64 q heads on 8 kv heads, 8 layers' worth) under the 768-node
+        # tree at M=1024: per rank 32 q heads / 4 kv heads, 6 query tiles x 8 KV tiles in the attention kernel
+        gm = cases.load_growmap("L40_growmaps/L40-CNN-7b-70b-stochastic.pt")
+        M, plen, iters = 1024, 128, 3
+        tspec = "random-init:llama-2-70b-8l:2"
+    target_tp = GraphInferenceEngineTG(M, tspec, device=dev, tp_group=grp)
     if rank != 0:
         TPFollower(target_tp, gm, False, M, dev, grp).serve()
         os._exit(0)
     try:
         draft = GraphInferenceEngine(M, {"config": dcfg, "state_dict": dw}, device=dev)
         draft2 = GraphInferenceEngine(M, {"config": dcfg, "state_dict": dw}, device=dev)
-        target_1 = GraphInferenceEngineTG(M, {"config": tcfg, "state_dict": tw}, device=dev)
+        target_1 = GraphInferenceEngineTG(M, tspec, device=dev)
         attach_tp(draft, target_tp, grp)
         prompt = cases.make_prompt(25, plen).to(dev)
         buf = lambda: dict(attn_mask=torch.full((M, M), torch.finfo(torch.float16).min, dtype=torch.float16, device=dev),
@@ -82,12 +90,13 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_tp2_decode_matches_single_gpu():
+@pytest.mark.parametrize("variant", ["tiny", "70b-8l"])
+def test_tp2_decode_matches_single_gpu(variant):
     import torch.multiprocessing as mp
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, variant)) for r in range(2)]
     [p.start() for p in procs]
     res = q.get(timeout=600)
     [p.join(60) for p in procs]
@@ -95,7 +104,14 @@ def test_tp2_decode_matches_single_gpu():
     assert len(res) >= 2
     tag, err, _ = res.pop()
     assert tag == "peer_error" and err == 0, "fused all-reduce handshake timed out"
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "tp_parity_test.log"), "a") as f:
+        f.write(f"{variant}: peer_error={err} " + " ".join(f"[iter {it} same={same} rel={rel:.3e}]" for it, same, rel in res) + "\n")
+    # logits are comparable while both runs hold the same token tree (up to and including the first differing iteration)
     for it, same, rel in res:
-        assert rel < 5e-3, f"iter {it}: TP-2 target logits differ from TP-1 by {rel} (relative to max |logit|)"
+        assert rel < 2e-3, f"iter {it}: TP-2 target logits differ from TP-1 by {rel} (relative to max |logit|)"
+        if not same:
+            break
     assert res[0][1], "first iteration: TP-2 accept length / tokens differ from single GPU"
     assert sum(1 for r in res if r[1]) >= 2, f"TP-2 decode forked too early: {res}"

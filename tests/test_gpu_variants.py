@@ -20,6 +20,9 @@ from test_gpu_decode import (DEV, F16, REL_TOL, _buffers, _engines, _explained_a
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 VAR = torch.load(os.path.join(G, "variants_golden.pt"))
+VAR.update(torch.load(os.path.join(G, "sweep_golden.pt")))
+CASES = dict(cases.VARIANT_CASES)
+CASES.update(cases.SWEEP_CASES)            # tests/run.sh tree shapes (K chains of length L) for the same policies
 
 
 def _make(mode, draft, target, prompt, gm, M):
@@ -37,10 +40,10 @@ def _oracles(dkey, tkey, M):
     return O.EngineOracle(O.LlamaOracle(dcfg, dw, M, "FI")), O.EngineOracle(O.LlamaOracle(tcfg, tw, M, "TG"))
 
 
-@pytest.mark.parametrize("name", ["greedys_4x4", "greedys_same_4x4"])
+@pytest.mark.parametrize("name", ["greedys_4x4", "greedys_same_4x4", "sweep_greedys_5x8"])
 @pytest.mark.parametrize("graphs", [True, False])
 def test_greedys_tree_lockstep(name, graphs):
-    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = cases.VARIANT_CASES[name]
+    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = CASES[name]
     gm = cases.load_growmap(gm_name)
     S = gm["size"]
     prompt = cases.make_prompt(pseed, plen)
@@ -95,10 +98,11 @@ def test_greedys_tree_lockstep(name, graphs):
     assert matched >= 1, f"{name}: not a single iteration matched the oracle"
 
 
-@pytest.mark.parametrize("name", ["specinfer_8x8", "specinfer_same_8x8"])
+@pytest.mark.parametrize("name", ["specinfer_8x8", "specinfer_same_8x8"] +
+                         [n for n, c in cases.SWEEP_CASES.items() if c[1] == "specinfer"])
 @pytest.mark.parametrize("graphs", [True, False])
 def test_specinfer_tree_lockstep(name, graphs):
-    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = cases.VARIANT_CASES[name]
+    gm_name, mode, dkey, tkey, M, pseed, plen, iters, rng_seed = CASES[name]
     gm = cases.load_growmap(gm_name)
     S = gm["size"]
     prompt = cases.make_prompt(pseed, plen)
