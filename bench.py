@@ -126,16 +126,21 @@ def run_reference_gpu(config, steps, warmup, n_parity, trace_path, timeout=900):
     """The unmodified reference on this GPU (oracle/ref_gpu.py, separate process).  -> its JSON dict."""
     if not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "utils.py")):
         return {"impl": "reference_gpu", "unavailable": "oracle/_ref missing (tools/vendor_ref.py runs in the build container)"}
-    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_gpu.py"), "--spec", json.dumps(ref_spec(config)), "--steps",
-           str(steps), "--warmup", str(warmup), "--parity", str(n_parity), "--trace", trace_path]
-    try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, cwd=ROOT)
-        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-        if not lines:
-            return {"impl": "reference_gpu", "unavailable": f"rc={r.returncode}: {r.stderr[-400:]}"}
-        return json.loads(lines[-1])
-    except Exception as e:
-        return {"impl": "reference_gpu", "unavailable": f"{type(e).__name__}: {e}"}
+    last = None
+    for sdp in ("no_cudnn", "math"):      # a CUDA fault poisons the process: every attempt is a fresh one
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_gpu.py"), "--spec", json.dumps(ref_spec(config)), "--steps",
+               str(steps), "--warmup", str(warmup), "--parity", str(n_parity), "--trace", trace_path, "--sdp", sdp]
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, cwd=ROOT)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            last = json.loads(lines[-1]) if lines else {"impl": "reference_gpu", "unavailable": f"rc={r.returncode}: {r.stderr[-400:]}"}
+        except Exception as e:
+            last = {"impl": "reference_gpu", "unavailable": f"{type(e).__name__}: {e}"}
+        if "unavailable" not in last:
+            return last
+        last["unavailable"] = f"[sdpa={sdp}] " + last["unavailable"][:300]
+        last.pop("traceback", None)
+    return last
 
 
 def first_iteration_trace(new_tree, draft, target, S, prefix, n_prompts):

@@ -135,7 +135,16 @@ def testbed_setup(ref, draft, grow_map, M, T, greedy, device):
     return residual_graph, sampling_callables, sample_gather_indices
 
 
-def run(spec, steps, warmup, n_parity, trace_path, device="cuda:0"):
+def run(spec, steps, warmup, n_parity, trace_path, device="cuda:0", sdp="no_cudnn"):
+    # SDPA backend selection (not a code change): the reference was written for torch 2.1.2, whose dispatcher knew flash /
+    # mem-efficient / math.  torch 2.11 adds a cuDNN backend that faults ("misaligned address") on the strided,
+    # arbitrarily offset fp16 mask views Tree/SpecTree.py:116-123 hands to F.scaled_dot_product_attention.
+    if str(device).startswith("cuda"):
+        if sdp in ("no_cudnn", "math"):
+            torch.backends.cuda.enable_cudnn_sdp(False)
+        if sdp == "math":
+            torch.backends.cuda.enable_flash_sdp(False)
+            torch.backends.cuda.enable_mem_efficient_sdp(False)
     ref = load_reference()
     sys.path.append(ROOT)                           # appended: Engine / Tree / utils stay the reference's
     from sequoia_b200.model import NAMED_CONFIGS, _RandomInit, full_state_dict
@@ -242,7 +251,7 @@ def run(spec, steps, warmup, n_parity, trace_path, device="cuda:0"):
             "how": "unmodified reference (oracle/_ref) on this GPU through tests/testbed.py's own setup: its CUDA graphs for "
                    "the draft widths / sampling / residual, eager target forward, host accept loop; same random-init "
                    "weights, prompts and per-prompt seeds as the sequoia_b200 arm",
-            "torch": torch.__version__}
+            "torch": torch.__version__, "sdpa_backends": sdp}
 
 
 def main():
@@ -253,9 +262,10 @@ def main():
     ap.add_argument("--parity", type=int, default=4)
     ap.add_argument("--trace", default="")
     ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--sdp", default="no_cudnn", choices=["auto", "no_cudnn", "math"])
     a = ap.parse_args()
     try:
-        out = run(json.loads(a.spec), a.steps, a.warmup, a.parity, a.trace, a.device)
+        out = run(json.loads(a.spec), a.steps, a.warmup, a.parity, a.trace, a.device, a.sdp)
     except Exception as e:  # the bench line must survive a reference that does not run on this software stack
         import traceback
         out = {"impl": "reference_gpu", "unavailable": f"{type(e).__name__}: {e}", "traceback": traceback.format_exc()[-1500:]}

@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(256) rope_kv_append_kernel(
     __half* __restrict__ qkv, int ld, int H, int Hkv, int D, const __half* __restrict__ cosc,
     const __half* __restrict__ sinc, const int64_t* __restrict__ position_ids, const int64_t* __restrict__ storage_ids,
     const int32_t* __restrict__ state, int n0, __half* __restrict__ k_layer, __half* __restrict__ v_layer, int M) {
+  // let a programmatically dependent attention launch start its prologue (it waits for this grid's completion itself)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int r = blockIdx.x;
   const int base = row_base(state, n0);
   const int64_t pos = position_ids[base + r];

@@ -286,6 +286,48 @@ def test_tree_attention(D, H, Hkv, M, P, gm, mode, impl):
     assert err < 4e-3, f"dense mask: max abs err {err}"
 
 
+@pytest.mark.parametrize("D,H,Hkv,M,P,boost", [
+    (128, 4, 4, 640, 400, 14.0),      # 1 q tile, 5 KV tiles, Z=5 -> one tile per split (no in-CTA loop), boosted tail
+    (128, 40, 40, 640, 400, 14.0),    # Z=3 -> two tiles per CTA: the in-CTA lazy rescale fires on the boosted tile
+    (64, 12, 12, 2048, 1800, 10.0),   # max_length beyond 1024: 15 active KV tiles, chunks of 2 tiles over 8 splits
+    (128, 8, 1, 2048, 1500, 0.0),     # GQA 8:1 beyond 1024 keys
+])
+def test_tree_attention_long_kv_and_lazy_rescale(D, H, Hkv, M, P, boost):
+    """The in-CTA KV loop: any max_length, and the lazy rescale of the tensor-memory accumulator (the reference maximum only
+    moves when it grows by > 2^8): keys of the LAST visible tiles are scaled up so that their scores dwarf the earlier
+    tiles' running maximum."""
+    from sequoia_b200 import ops as sops
+    from sequoia_b200.tree import pack_tree_mask
+    grow = cases.load_growmap("A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt")
+    S = grow["size"]
+    g = torch.Generator().manual_seed(11)
+    L, layer = 1, 0
+    ld = (H + 2 * Hkv) * D
+    kc = torch.randn(L, 1, Hkv, M, D, generator=g)
+    vc = torch.randn(L, 1, Hkv, M, D, generator=g).to(F16)
+    kv_len = P - 1 + S
+    if boost:
+        kc[..., kv_len - 200:kv_len, :] *= boost / math.sqrt(D) * 4       # later keys: much larger |score|
+    kc = kc.to(F16)
+    vis = O.visible_from_rule(M, P, grow["mask"])[P - 1:P - 1 + S, :kv_len]
+    qkv = torch.randn(M, ld, generator=g).to(F16)
+    dq, dk, dv = qkv.to(DEV), kc.to(DEV), vc.to(DEV)
+    out = torch.zeros(M, H * D, dtype=F16, device=DEV)
+    plan = sops.AttnPlan(dq, M, H, Hkv, D, dk, dv, out)
+    bits = pack_tree_mask(grow["mask"]).to(DEV)
+    state = torch.zeros(16, dtype=torch.int32, device=DEV)
+    state[0] = P
+    ref = _attn_reference(qkv[:S, :H * D].view(S, H, D), kc[layer, 0, :, :kv_len], vc[layer, 0, :, :kv_len], vis, H, Hkv, D)
+    for impl in (1, 0):
+        out.zero_()
+        sops.tree_attn(plan, layer, S, state=state, n0=0, kv_end=S, prefix_len=P, tree_bits=bits, tree_words=bits.shape[1],
+                       tree_size=S, impl=impl)
+        torch.cuda.synchronize()
+        assert plan.error() == 0
+        err = (out[:S].float().cpu().view(S, H, D) - ref).abs().max().item()
+        assert err < 6e-3, f"impl {impl}: max abs err {err}"          # fp16 P (up to 2^8 under a stale maximum) and output
+
+
 # ------------------------------------------------------------------------------------------------ accept walk
 def _oracle_engines(dkey, tkey, M):
     dcfg, dw = cases.model_weights(dkey)

@@ -1,16 +1,27 @@
-"""Stand-alone driver of the verify-attention kernel at config-2 shape (for ncu captures and quick timing)."""
-import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+"""Stand-alone driver of the verify-attention kernel at a named config's shape (ncu captures, quick timing, phase stamps).
+PROBE_CFG = c2 (default) | c3 | c4tp8 (one TP-8 rank of 70B) | c4 (unsharded 70B) | c4draft (7B draft, one level)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import torch
 from sequoia_b200 import ops
 from sequoia_b200.tree import pack_tree_mask
 
-H, Hkv, D, M, L = 32, 32, 128, 384, int(os.environ.get("PROBE_L", "32"))
+CFG = {  # H, Hkv, D, M, growmap, P, rows (None = whole tree), n0
+    "c2": (32, 32, 128, 384, "A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt", 193, None, 0),
+    "c3": (40, 40, 128, 384, "L40_growmaps/8x8-tree.pt", 193, None, 0),
+    "c4tp8": (8, 1, 128, 1024, "L40_growmaps/L40-CNN-7b-70b-stochastic.pt", 193, None, 0),
+    "c4": (64, 8, 128, 1024, "L40_growmaps/L40-CNN-7b-70b-stochastic.pt", 193, None, 0),
+    "c4draft": (32, 32, 128, 1024, "L40_growmaps/L40-CNN-7b-70b-stochastic.pt", 193, 82, 300),
+}
+name = os.environ.get("PROBE_CFG", "c2")
+H, Hkv, D, M, gmp, P, rows, n0 = CFG[name]
+L = int(os.environ.get("PROBE_L", "32" if name != "c4" else "8"))
 dev = "cuda:0"
-gm = torch.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                             "A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt"))
+gm = torch.load(os.path.join(ROOT, gmp))
 S = gm["size"]
-P = 193
+n = rows or S
+kv_end = (n0 + n) if rows else S
 qkv = torch.randn(M, (H + 2 * Hkv) * D, device=dev, dtype=torch.float16)
 kc = torch.randn(L, 1, Hkv, M, D, device=dev, dtype=torch.float16)
 vc = torch.randn(L, 1, Hkv, M, D, device=dev, dtype=torch.float16)
@@ -21,8 +32,10 @@ state = torch.zeros(16, dtype=torch.int32, device=dev)
 state[0] = P
 impl = int(os.environ.get("PROBE_IMPL", "0"))
 
+
 def call(l):
-    ops.tree_attn(plan, l % L, S, state=state, n0=0, kv_end=S, tree_bits=bits, tree_words=bits.shape[1], tree_size=S, impl=impl)
+    ops.tree_attn(plan, l % L, n, state=state, n0=n0, kv_end=kv_end, tree_bits=bits, tree_words=bits.shape[1], tree_size=S, impl=impl)
+
 
 for i in range(8):
     call(i)
@@ -37,7 +50,12 @@ e0.record()
 for _ in range(5):
     g.replay()
 e1.record(); e1.synchronize()
-print("attention us/launch:", e0.elapsed_time(e1) / (10 * L) * 1e3, "plan error", plan.error())
+us = e0.elapsed_time(e1) / (10 * L) * 1e3
+kv = P - 1 + kv_end
+byt = 2 * D * 2 * (Hkv * kv + H * n)
+fl = 4 * H * n * kv * D
+print(f"{name}: attention {us:.2f} us/launch  ({byt / us / 1e3:.0f} GB/s algorithmic, {fl / us / 1e6:.1f} TFLOP/s)  H={H} Hkv={Hkv} q={n} kv={kv} "
+      f"plan error {plan.error()}")
 
 if os.environ.get("SQ_ATTN_TIMING"):
     import ctypes, numpy as np
@@ -46,10 +64,10 @@ if os.environ.get("SQ_ATTN_TIMING"):
     buf = (ctypes.c_longlong * 128)()
     rc = _lib.load().sq_attn_plan_debug_times(plan.handle, buf)
     t = np.array(list(buf)).reshape(8, 16)
-    names = ["start", "alloc+sync", "TMA q,k landed", "MMA1 done", "softmax done", "MMA2 done", "epilogue+dealloc", "cluster sync 1", "reduction", "cluster sync 2"]
-    for s_ in range(3):
+    nm = {0: "P known", 1: "prologue sync", 2: "S0 ready", 4: "softmax0 done", 5: "O done", 10: "O staged+dealloc", 6: "pushed",
+          7: "cluster sync", 9: "weights", 8: "end"}
+    for s_ in range(8):
         row = t[s_]
-        order = [0, 1, 2, 3, 4, 5, 10, 6, 7, 9, 8]
-        nm = {0: "start", 1: "alloc+mask+sync", 2: "TMA q,k landed", 3: "MMA1 done", 4: "softmax done", 5: "MMA2 done",
-              10: "O staged+dealloc", 6: "pushed", 7: "cluster sync", 9: "weights", 8: "reduced"}
-        print("split", s_, " ".join(f"{nm[k]}:+{int(row[k]-row[0])}" for k in order))
+        if row[0] == 0:
+            continue
+        print("split", s_, " ".join(f"{nm[k]}:+{int(row[k] - row[0])}" for k in (0, 1, 2, 4, 5, 10, 6, 7, 9, 8) if row[k]))
