@@ -17,7 +17,7 @@
 struct sq_gemm_plan {
   CUtensorMap tm_a, tm_w;
   __half* c;
-  int ldc, n_max, N, K, bn, split, stages;
+  int ldc, n_max, N, K, bn, split, stages, mc, pdl;
   int* err_flag;
 };
 
@@ -32,11 +32,13 @@ struct GemmArgs {
 constexpr int G_BK = 64;
 constexpr int G_THREADS = 192;       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
 
+__host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
+
 template <int BN, int STAGES, int SPLIT>
 struct GemmSmem {
   static constexpr int A_BYTES = 128 * 128;            // 128 rows x 64 halfs
   static constexpr int W_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + ((W_BYTES + 1023) / 1024) * 1024;   // stages stay 1024 B aligned (SW128)
   static constexpr int OFF_BAR = STAGES * STAGE_BYTES; // full[STAGES], empty[STAGES], tmem_full, tmem ptr
   static constexpr int OFF_RED = OFF_BAR + 256;        // split-K: SPLIT slots x (128/SPLIT rows) x (BN+4) floats
   static constexpr int R_STRIDE = BN + 4;
@@ -44,15 +46,31 @@ struct GemmSmem {
   static constexpr int TOTAL = OFF_RED + RED_BYTES;
 };
 
-template <int BN, int STAGES, int SPLIT>
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(tm), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+// MC = CTAs (along N) that share one activation K-slab: each loads 128/MC of its rows and multicasts them to all.
+template <int BN, int STAGES, int SPLIT, int MC>
 __global__ void __launch_bounds__(G_THREADS, 1)
     gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, GemmArgs g) {
+  // cluster (MC, SPLIT): rank = mcr + MC * ks.  CTAs with the same ks share the activation slab (multicast group); CTAs
+  // with the same mcr hold the K-splits of one output tile (DSMEM reduction group).
   using SM = GemmSmem<BN, STAGES, SPLIT>;
+  constexpr int TCOLS = tmem_cols_for(BN);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * BN;
-  const int ks = blockIdx.y;                               // K split index == rank in the cluster
+  const int ks = blockIdx.y;                               // K split index == rank in the (1, SPLIT) cluster
+  const int mcr = (MC > 1) ? (int)(blockIdx.x % MC) : 0;   // rank in the (MC, 1) cluster
   const int kb0 = ks * g.kb_per_split;
   const int nkb = g.kb_per_split;
   const uint32_t s_base = ptx::smem_u32(smem);
@@ -63,31 +81,47 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(bar_full + 8 * s, 1);
-      ptx::mbar_init(bar_empty + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, MC);               // every CTA that received this slot's A rows must release it
     }
     ptx::mbar_init(bar_tmem, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), BN);
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), TCOLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (MC > 1)   // the peers' barriers must be initialised before any multicast / remote arrive can target them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+      // Weights do not depend on the previous kernel: under programmatic dependent launch the first ring of weight
+      // tiles streams in while that kernel is still running; only the activation loads wait for it.
+      const int pre = nkb < STAGES ? nkb : STAGES;
+      for (int kb = 0; kb < pre; ++kb) {
+        const uint32_t sa = s_base + kb * SM::STAGE_BYTES, sw = sa + SM::A_BYTES;
+        ptx::mbar_expect_tx(bar_full + 8 * kb, SM::A_BYTES + SM::W_BYTES);
+        ptx::tma_load_2d(sw, &tm_w, bar_full + 8 * kb, (kb0 + kb) * G_BK, n0);
+      }
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        ptx::mbar_wait_one(bar_empty + 8 * stage, phase ^ 1, g.err_flag, 11);     // slot free (fresh barrier passes)
         const uint32_t sa = s_base + stage * SM::STAGE_BYTES, sw = sa + SM::A_BYTES;
-        ptx::mbar_expect_tx(bar_full + 8 * stage, SM::STAGE_BYTES);
-        ptx::tma_load_2d(sa, &tm_a, bar_full + 8 * stage, (kb0 + kb) * G_BK, 0);
-        ptx::tma_load_2d(sw, &tm_w, bar_full + 8 * stage, (kb0 + kb) * G_BK, n0);
+        if (kb >= pre) {
+          ptx::mbar_wait_one(bar_empty + 8 * stage, phase ^ 1, g.err_flag, 11);   // slot free in EVERY CTA of the cluster
+          ptx::mbar_expect_tx(bar_full + 8 * stage, SM::A_BYTES + SM::W_BYTES);
+          ptx::tma_load_2d(sw, &tm_w, bar_full + 8 * stage, (kb0 + kb) * G_BK, n0);
+        }
+        if (MC == 1) ptx::tma_load_2d(sa, &tm_a, bar_full + 8 * stage, (kb0 + kb) * G_BK, 0);
+        else tma_load_2d_mc(sa + mcr * (SM::A_BYTES / MC), &tm_a, bar_full + 8 * stage, (kb0 + kb) * G_BK, mcr * (128 / MC),
+                            (uint16_t)(((1u << MC) - 1u) << (MC * ks)));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -104,7 +138,9 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 #pragma unroll
         for (int k = 0; k < G_BK / 16; ++k)
           ptx::mma_ss(tmem, umma_desc(sa + k * 32, 16, 1024), umma_desc(sw + k * 32, 16, 1024), idesc, (kb | k) != 0);
-        ptx::tc_commit(bar_empty + 8 * stage);                                     // frees the slot when the MMAs retire
+        // frees the slot when the MMAs retire -- in every CTA whose multicast writes into this CTA's slot
+        if (MC == 1) ptx::tc_commit(bar_empty + 8 * stage);
+        else tc_commit_mc(bar_empty + 8 * stage, (uint16_t)(((1u << MC) - 1u) << (MC * ks)));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       ptx::tc_commit(bar_tmem);                                                    // accumulator complete
@@ -122,7 +158,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       for (int j = 0; j < BN / 32; ++j) {
         uint32_t r[32];
         ptx::tmem_ld32(tmem + lane_base + j * 32, r);
-        if (row < g.n) {
+        if (row < g.n && n0 + j * 32 < g.N) {               // (ragged last tile: N is a multiple of 32)
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
             Pack8 o;
@@ -137,7 +173,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       constexpr int RPC = 128 / SPLIT;
       const uint32_t owner = (uint32_t)(row / RPC);
       uint32_t dst;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(s_base + SM::OFF_RED), "r"(owner));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(s_base + SM::OFF_RED), "r"((uint32_t)mcr + MC * owner));
       dst += (uint32_t)((ks * RPC + row % RPC) * SM::R_STRIDE * 4);
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
@@ -153,10 +189,14 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem, BN);
+  if (warp == 1) ptx::tmem_dealloc(tmem, TCOLS);
+
+  // (MC > 1: no CTA may leave while a peer can still multicast into its slots / arrive on its barriers;
+  //  SPLIT > 1: the partial rows of every K-split must have landed in the owners' shared memory)
+  if (MC > 1 || SPLIT > 1)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
   if (SPLIT > 1) {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     // owner CTA ks reduces rows [ks*RPC, (ks+1)*RPC): sum of the SPLIT slots in split order, fp16 out
     constexpr int RPC = 128 / SPLIT;
     constexpr int CPR = BN / 4;
@@ -209,26 +249,59 @@ static int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t
   return SQ_OK;
 }
 
+// Tile selection: put a CTA on (nearly) every SM with the widest N tile that allows -- per-SM ingest, not HBM, is what
+// limits a 128-row weight stream, and the activation tile every CTA re-reads is pure overhead: a wider BN and a 2-CTA
+// multicast of the activation slab both raise the weight share of each SM's ingest.
+static void choose_tiles(sq_gemm_plan* p) {
+  const int N = p->N, kb = p->K / 64;
+  const int cands[] = {256, 224, 192, 160, 128, 96, 64};
+  int best_bn = 128, best_split = 1, best_mc = 1;
+  double best_score = -1.0;
+  for (int bn : cands) {
+    const int tiles = (N + bn - 1) / bn;
+    for (int split : {1, 2, 4}) {
+      if (kb % split) continue;
+      if (split > 1 && (bn > 128 || N % bn)) continue;       // DSMEM reduction buffers: BN <= 128, no ragged tile
+      const int ctas = tiles * split;
+      if (ctas > 148) continue;
+      for (int mc : {1, 2}) {
+        if (mc == 2 && (tiles % 2 || (split > 1 && bn == 96))) continue;       // (combinations in sq_gemm_run's table)
+        // modelled weight bandwidth ~ CTAs x weight share of the per-SM ingest; split-K pays a reduction tail
+        const double a_share = 128.0 / mc, share = bn / (bn + a_share);
+        double score = ctas * share;
+        if (split > 1) score *= 0.85;
+        if (score > best_score) { best_score = score; best_bn = bn; best_split = split; best_mc = mc; }
+      }
+    }
+  }
+  p->bn = best_bn; p->split = best_split; p->mc = best_mc;
+}
+
 extern "C" int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N,
                                    int K, sq_half* c, int ldc, int* err_flag) {
   SQ_CHECK_ARG(plan && a && w && c, "sq_gemm_plan_create: null pointer");
-  SQ_CHECK_ARG(K % 64 == 0 && N % 128 == 0 && lda % 8 == 0 && ldc % 8 == 0, "sq_gemm_plan_create: K %% 64, N %% 128");
+  SQ_CHECK_ARG(K % 64 == 0 && N % 32 == 0 && lda % 8 == 0 && ldc % 8 == 0, "sq_gemm_plan_create: K %% 64, N %% 32");
   sq_gemm_plan* p = new sq_gemm_plan();
   p->c = (__half*)c; p->ldc = ldc; p->n_max = n_max; p->N = N; p->K = K; p->err_flag = err_flag;
-  const int tiles128 = N / 128;
   const int kb = K / 64;
-  // one wave on 148 SMs: wide outputs use 256-wide tiles when that fits one wave; narrow outputs split K over a cluster
-  if (tiles128 > 148 && N % 256 == 0 && N / 256 <= 148) { p->bn = 256; p->split = 1; p->stages = 4; }
-  else if (tiles128 <= 37 && kb % 4 == 0) { p->bn = 128; p->split = 4; p->stages = 4; }
-  else if (tiles128 <= 74 && kb % 2 == 0) { p->bn = 128; p->split = 2; p->stages = 4; }
-  else { p->bn = 128; p->split = 1; p->stages = 6; }
-  const char* force = getenv("SQ_GEMM_FORCE");          // debugging: "bn,split"
+  choose_tiles(p);
+  const char* force = getenv("SQ_GEMM_FORCE");          // tuning / debugging: "bn,split,mc"
   if (force) {
-    int fb = 0, fs = 0;
-    if (sscanf(force, "%d,%d", &fb, &fs) == 2 && (fb == 128 || fb == 256) && (fs == 1 || fs == 2 || fs == 4) &&
-        N % fb == 0 && kb % fs == 0) { p->bn = fb; p->split = fs; p->stages = (fb == 128 && fs == 1) ? 6 : 4; }
+    int fb = 0, fs = 0, fm = 1;
+    const int nf = sscanf(force, "%d,%d,%d", &fb, &fs, &fm);
+    const bool bn_ok = fb == 64 || fb == 96 || fb == 128 || fb == 160 || fb == 192 || fb == 224 || fb == 256;
+    if (nf >= 2 && bn_ok && (fs == 1 || fs == 2 || fs == 4) && kb % fs == 0 && (fm == 1 || fm == 2) &&
+        !(fs > 1 && (fb > 128 || N % fb)) && !(fm == 2 && ((N + fb - 1) / fb) % 2)) {
+      p->bn = fb; p->split = fs; p->mc = fm;
+    }
   }
-  int rc = encode_2d(&p->tm_a, a, (uint64_t)K, (uint64_t)n_max, (uint64_t)lda * 2, 64, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  {
+    const char* pe = getenv("SQ_PDL");
+    p->pdl = (pe && atoi(pe)) ? 1 : 0;
+  }
+  p->stages = p->split > 1 ? 4 : (p->bn >= 224 ? 4 : p->bn >= 160 ? 5 : p->bn >= 96 ? 6 : 8);   // == the dispatch table below
+  int rc = encode_2d(&p->tm_a, a, (uint64_t)K, (uint64_t)n_max, (uint64_t)lda * 2, 64, (uint32_t)(128 / p->mc),
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   if (!rc) rc = encode_2d(&p->tm_w, w, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 64, (uint32_t)p->bn, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc) { delete p; return rc; }
   *plan = p;
@@ -240,29 +313,35 @@ extern "C" int sq_gemm_plan_destroy(sq_gemm_plan* plan) {
   return SQ_OK;
 }
 
-template <int BN, int STAGES, int SPLIT>
+template <int BN, int STAGES, int SPLIT, int MC>
 static int launch_gemm(sq_gemm_plan* p, GemmArgs& g, cudaStream_t st) {
   using SM = GemmSmem<BN, STAGES, SPLIT>;
   constexpr int smem = SM::TOTAL + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, SPLIT, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("sq_gemm: smem attr: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
     attr = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p->N / BN, SPLIT, 1);
+  cfg.gridDim = dim3((p->N + BN - 1) / BN, SPLIT, 1);
   cfg.blockDim = dim3(G_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 1;
+  at[0].val.clusterDim.x = MC;
   at[0].val.clusterDim.y = SPLIT;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, STAGES, SPLIT>, p->tm_a, p->tm_w, g);
+  if (p->pdl) {
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, STAGES, SPLIT, MC>, p->tm_a, p->tm_w, g);
   if (e != cudaSuccess) { set_error("sq_gemm: launch failed: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
   SQ_CHECK_LAUNCH("sq_gemm");
   return SQ_OK;
@@ -277,13 +356,21 @@ extern "C" int sq_gemm_run(sq_gemm_plan* plan, int n, void* stream) {
   g.kb_per_split = plan->K / 64 / plan->split;
   g.err_flag = plan->err_flag;
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan->bn == 256) return launch_gemm<256, 4, 1>(plan, g, st);
-  if (plan->split == 4) return launch_gemm<128, 4, 4>(plan, g, st);
-  if (plan->split == 2) return launch_gemm<128, 4, 2>(plan, g, st);
-  return launch_gemm<128, 6, 1>(plan, g, st);
+  const int bn = plan->bn, sp = plan->split, mc = plan->mc;
+#define SQ_G(BN_, ST_, SP_, MC_) if (bn == BN_ && sp == SP_ && mc == MC_) return launch_gemm<BN_, ST_, SP_, MC_>(plan, g, st)
+  SQ_G(256, 4, 1, 1); SQ_G(256, 4, 1, 2);
+  SQ_G(224, 4, 1, 1); SQ_G(224, 4, 1, 2);
+  SQ_G(192, 5, 1, 1); SQ_G(192, 5, 1, 2);
+  SQ_G(160, 5, 1, 1); SQ_G(160, 5, 1, 2);
+  SQ_G(128, 6, 1, 1); SQ_G(128, 6, 1, 2); SQ_G(128, 4, 2, 1); SQ_G(128, 4, 4, 1); SQ_G(128, 4, 2, 2); SQ_G(128, 4, 4, 2);
+  SQ_G(96, 6, 1, 1); SQ_G(96, 6, 1, 2); SQ_G(96, 4, 2, 1); SQ_G(96, 4, 4, 1);
+  SQ_G(64, 8, 1, 1); SQ_G(64, 8, 1, 2); SQ_G(64, 4, 2, 1); SQ_G(64, 4, 4, 1); SQ_G(64, 4, 2, 2); SQ_G(64, 4, 4, 2);
+#undef SQ_G
+  set_error("sq_gemm_run: no kernel for bn=%d split=%d mc=%d", bn, sp, mc);
+  return SQ_ERR_UNSUPPORTED;
 }
 
 extern "C" int sq_gemm_plan_info(sq_gemm_plan* plan, int* bn, int* split, int* stages) {
-  *bn = plan->bn; *split = plan->split; *stages = plan->stages;
+  *bn = plan->bn; *split = plan->split; *stages = plan->stages + 100 * plan->mc;
   return SQ_OK;
 }

@@ -14,3 +14,10 @@ if [ $rc -eq 0 ]; then
   SQ_PDL=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-reference-gpu --no-cpu-baseline > gpurun_out/r2b_bench_c2_pdl.json 2> gpurun_out/r2b_bench_c2_pdl.err; echo "pdl bench rc=$?"
   head -c 600 gpurun_out/r2b_bench_c2_pdl.json; tail -3 gpurun_out/r2b_bench_c2_pdl.err
 fi
+# GEMM v2 sweep: default tile choice + forced alternatives (bn,split,mc)
+timeout 300 python tools/gemm_probe.py > gpurun_out/r2b_gemm_default.log 2>&1
+for f in "qkv:128,1,2" "qkv:192,1,2" "qkv:96,1,1" "gate_up:256,1,2" "gate_up:160,1,1" "gate_up:128,1,1" "o:128,4,1" "o:64,4,2" "o:64,2,2" "down:128,4,1" "down:64,4,2" "lm_head:256,1,1"; do
+  SQ_GEMM_FORCE=${f#*:} PROBE_ONLY=${f%%:*} timeout 120 python tools/gemm_probe.py >> gpurun_out/r2b_gemm_forced.log 2>&1
+done
+SQ_PDL=1 timeout 300 python tools/gemm_probe.py > gpurun_out/r2b_gemm_pdl.log 2>&1
+cat gpurun_out/r2b_gemm_default.log gpurun_out/r2b_gemm_forced.log gpurun_out/r2b_gemm_pdl.log | cut -c1-230
