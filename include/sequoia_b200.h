@@ -215,6 +215,14 @@ int sq_tp_allreduce_add_rmsnorm(sq_half* resid, const void* const* host_proj_ptr
                                 uint32_t* epoch, int rank, int N, const sq_half* weight, sq_half* out, int n,
                                 int hidden, float eps, void* stream);
 
+/* Two-shot variant (row r owned by rank r % N: the owner pulls the N partial rows, stores the fp16 sum into every rank's
+ * `red` buffer and raises a per-row flag; every rank then adds the residual and normalises from its local copy): per
+ * rank (N-1)/N of the payload pulled + (N-1)/N pushed instead of (N-1) x pulled.  host_red_ptrs[r] / host_rowflag_ptrs[r]:
+ * peer-mapped (n_max, hidden) fp16 buffer / n_max uint32 words on rank r; same epoch / flag words as the one-shot call. */
+int sq_tp_allreduce2_add_rmsnorm(sq_half* resid, const void* const* host_proj_ptrs, void* const* host_red_ptrs,
+                                 void* const* host_flag_ptrs, void* const* host_rowflag_ptrs, uint32_t* epoch, int rank,
+                                 int N, const sq_half* weight, sq_half* out, int n, int hidden, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "sq_tp_ipc_open": (i32, [vp, C.POINTER(vp)]),
     "sq_tp_ipc_close": (i32, [vp]),
     "sq_tp_allreduce_add_rmsnorm": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp]),
+    "sq_tp_allreduce2_add_rmsnorm": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

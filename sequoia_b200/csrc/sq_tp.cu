@@ -119,6 +119,156 @@ __global__ void __launch_bounds__(256) tp_allreduce_add_rmsnorm_kernel(TpArgs t,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Two-shot variant (reduce-scatter + all-gather in ONE kernel) for N >= 4 and / or large payloads: the one-shot kernel
+// above makes every rank pull (N-1) x the payload (7 x 12.6 MB per reduction at TP-8 on the 70B shapes); here row r is
+// OWNED by rank r % N: the owner's CTA pulls the N partial rows, sums them in fp32 in rank order, rounds to fp16 and
+// STORES the reduced row into the `red` buffer of every rank (st.relaxed.sys over NVLink), then raises a per-row flag on
+// every rank (fence + st.release.sys).  Every rank's CTA for that row waits for the flag (owners skip the wait), reads the
+// reduced row from its LOCAL memory and does residual add + RMSNorm.  Per rank and reduction: (N-1)/N of the payload
+// pulled + (N-1)/N pushed, independent of N.  Buffers alternate A/B exactly like the partial buffers (the epoch handshake
+// of the next reduction proves every rank finished the previous one), so a row flag can never be two epochs ahead of a
+// reader.  Block b of rank k handles an OWNED row first (b < owned rows), so an owner never queues behind a waiter.
+struct Tp2Args {
+  const __half* proj[8];     // partial GEMM outputs of rank 0..N-1
+  __half* red[8];            // reduced rows, (n_max, hidden) fp16 on every rank
+  uint32_t* flags[8];        // epoch flags (as in TpArgs)
+  uint32_t* rowflags[8];     // rowflags[r] = per-row epoch words living on rank r (n_max words)
+  uint32_t* epoch;
+  int rank, N;
+};
+
+__device__ __forceinline__ void st_relaxed_sys_v4(void* p, uint4 v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(256) tp_allreduce2_add_rmsnorm_kernel(Tp2Args t, __half* __restrict__ resid,
+                                                                        const __half* __restrict__ w,
+                                                                        __half* __restrict__ out, int n, int hidden, float eps) {
+  __shared__ float red[8];
+  const int tid = threadIdx.x, N = t.N, rank = t.rank;
+  // block -> row: owned rows (rank, rank+N, ...) first, then the others in order
+  const int n_own = (n - rank + N - 1) / N;                  // rows r < n with r % N == rank   (n > rank assumed below)
+  int r;
+  bool own;
+  {
+    const int b = blockIdx.x;
+    const int owned = (rank < n) ? n_own : 0;
+    if (b < owned) { r = rank + b * N; own = true; }
+    else {
+      // the (b - owned)-th row whose owner is another rank
+      const int j = b - owned;
+      // rows not owned: for every full group of N rows, N-1 of them; walk arithmetically
+      const int g = j / (N - 1), o = j % (N - 1);
+      r = g * N + (o < rank ? o : o + 1);
+      own = false;
+    }
+  }
+  const uint32_t e = t.epoch[0] + 1;
+  if (blockIdx.x == 0 && tid < N && tid != rank) st_release_sys(t.flags[tid] + rank, e);      // "my partial is ready"
+  const int nvec = hidden / 8;
+  Pack8 v[MAXV];
+  float ss = 0.f;
+  if (own) {
+    if (tid < N && tid != rank) {                            // every peer's partial of this epoch must be ready
+      const uint32_t* f = t.flags[rank] + tid;
+      const long long t0 = clock64();
+      while ((int32_t)(ld_acquire_sys(f) - e) < 0) {
+        if (clock64() - t0 > 4000000000LL) { atomicExch(t.epoch + 2, 1u); break; }
+      }
+    }
+    __syncthreads();
+    Pack8 part[MAXV][8];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = tid + i * 256;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        part[i][s].u = make_uint4(0, 0, 0, 0);
+        if (c < nvec && s < N) {
+          const uint4* src = reinterpret_cast<const uint4*>(t.proj[s] + (int64_t)r * hidden) + c;
+          part[i][s].u = (s == rank) ? *src : ld_relaxed_sys_v4(src);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = tid + i * 256;
+      if (c < nvec) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += h2f(part[i][s].h[j]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i].h[j] = f2h(acc[j]);          // the all-reduced projection output (fp16)
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < N && s != rank) st_relaxed_sys_v4(reinterpret_cast<uint4*>(t.red[s] + (int64_t)r * hidden) + c, v[i].u);
+      }
+    }
+    __syncthreads();                                          // every thread's remote stores are issued ...
+    if (tid < N && tid != rank) {
+      __threadfence_system();                                 // ... and ordered before the flag (cumulative release)
+      st_release_sys(t.rowflags[tid] + r, e);
+    }
+  } else {
+    if (tid == 0) {
+      const uint32_t* f = t.rowflags[rank] + r;
+      const long long t0 = clock64();
+      while ((int32_t)(ld_acquire_sys(f) - e) < 0) {
+        if (clock64() - t0 > 4000000000LL) { atomicExch(t.epoch + 2, 2u); break; }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = tid + i * 256;
+      if (c < nvec) v[i].u = ld_relaxed_sys_v4(reinterpret_cast<const uint4*>(t.red[rank] + (int64_t)r * hidden) + c);
+    }
+  }
+  // residual add + RMSNorm of row r (identical arithmetic to the one-shot kernel / sq_add_rmsnorm)
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    if (c < nvec) {
+      Pack8 a;
+      a.u = reinterpret_cast<const uint4*>(resid + (int64_t)r * hidden)[c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i].h[j] = f2h(h2f(a.h[j]) + h2f(v[i].h[j]));
+        const float f = h2f(v[i].h[j]);
+        ss += f * f;
+      }
+      reinterpret_cast<uint4*>(resid + (int64_t)r * hidden)[c] = v[i].u;
+    }
+  }
+  ss = block_sum<8>(ss, red);
+  const float inv = rsqrtf(ss / (float)hidden + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    if (c < nvec) {
+      Pack8 wv, o;
+      wv.u = reinterpret_cast<const uint4*>(w)[c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.h[j] = f2h(h2f(wv.h[j]) * h2f(f2h(h2f(v[i].h[j]) * inv)));
+      reinterpret_cast<uint4*>(out + (int64_t)r * hidden)[c] = o.u;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t ticket = atomicAdd(t.epoch + 1, 1u);
+    if (ticket == gridDim.x - 1) {
+      t.epoch[1] = 0u;
+      __threadfence();
+      t.epoch[0] = e;
+    }
+  }
+}
+
 }  // namespace sq
 
 using namespace sq;
@@ -179,5 +329,33 @@ extern "C" int sq_tp_allreduce_add_rmsnorm(sq_half* resid, const void* const* ho
   else if (nvec <= 1024) tp_allreduce_add_rmsnorm_kernel<4><<<n, 256, 0, st>>>(t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
   else tp_allreduce_add_rmsnorm_kernel<8><<<n, 256, 0, st>>>(t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
   SQ_CHECK_LAUNCH("sq_tp_allreduce_add_rmsnorm");
+  return SQ_OK;
+}
+
+extern "C" int sq_tp_allreduce2_add_rmsnorm(sq_half* resid, const void* const* host_proj_ptrs, void* const* host_red_ptrs,
+                                            void* const* host_flag_ptrs, void* const* host_rowflag_ptrs, uint32_t* epoch,
+                                            int rank, int N, const sq_half* weight, sq_half* out, int n, int hidden,
+                                            float eps, void* stream) {
+  SQ_CHECK_ARG(N >= 2 && N <= 8 && rank >= 0 && rank < N, "sq_tp_allreduce2_add_rmsnorm: bad rank/N %d/%d", rank, N);
+  SQ_CHECK_ARG(hidden % 8 == 0 && hidden <= 256 * 8 * 8, "sq_tp_allreduce2_add_rmsnorm: hidden=%d unsupported", hidden);
+  if (n == 0) return SQ_OK;
+  Tp2Args t;
+  for (int i = 0; i < 8; ++i) {
+    t.proj[i] = i < N ? (const __half*)host_proj_ptrs[i] : nullptr;
+    t.red[i] = i < N ? (__half*)host_red_ptrs[i] : nullptr;
+    t.flags[i] = i < N ? (uint32_t*)host_flag_ptrs[i] : nullptr;
+    t.rowflags[i] = i < N ? (uint32_t*)host_rowflag_ptrs[i] : nullptr;
+  }
+  t.epoch = epoch;
+  t.rank = rank;
+  t.N = N;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nvec = hidden / 8;
+  __half* r = (__half*)resid; const __half* w = (const __half*)weight; __half* o = (__half*)out;
+  if (nvec <= 256) tp_allreduce2_add_rmsnorm_kernel<1><<<n, 256, 0, st>>>(t, r, w, o, n, hidden, eps);
+  else if (nvec <= 512) tp_allreduce2_add_rmsnorm_kernel<2><<<n, 256, 0, st>>>(t, r, w, o, n, hidden, eps);
+  else if (nvec <= 1024) tp_allreduce2_add_rmsnorm_kernel<4><<<n, 256, 0, st>>>(t, r, w, o, n, hidden, eps);
+  else tp_allreduce2_add_rmsnorm_kernel<8><<<n, 256, 0, st>>>(t, r, w, o, n, hidden, eps);
+  SQ_CHECK_LAUNCH("sq_tp_allreduce2_add_rmsnorm");
   return SQ_OK;
 }

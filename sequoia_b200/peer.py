@@ -1,6 +1,7 @@
 """NVLink peer-memory buffers for the fused TP all-reduce kernel (csrc/sq_tp.cu).
 
-Each rank cudaMalloc's one block [partial A | partial B | flags | epoch], exports it with CUDA IPC, and maps every
+Each rank cudaMalloc's one block [partial A | partial B | reduced A | reduced B | flags | epoch | row flags A | row flags
+B], exports it with CUDA IPC, and maps every
 peer's block (cudaIpcOpenMemHandle, peer access over NVLink / NVSwitch).  torch sees the two partial buffers as ordinary
 fp16 tensors (zero-copy via __cuda_array_interface__), so the row-parallel GEMMs write their outputs straight into
 peer-visible memory with `torch.mm(..., out=...)`."""
@@ -30,7 +31,13 @@ class PeerBuffers:
         assert 2 <= self.N <= 8
         self.n_max, self.hidden = n_max, hidden
         part = n_max * hidden * 2
-        total = 2 * part + 2 * self.FLAG_BYTES
+        rowflag_bytes = ((n_max * 4 + 1023) // 1024) * 1024
+        total = 4 * part + 2 * self.FLAG_BYTES + 2 * rowflag_bytes
+        # one-shot (every rank pulls all partials) below 4 ranks, two-shot (reduce-scatter + all-gather in one kernel)
+        # from 4 ranks up; SQ_TP_SHOT=1|2 overrides
+        import os
+        shot = os.environ.get("SQ_TP_SHOT", "")
+        self.two_shot = (shot == "2") or (shot != "1" and self.N >= 4)
         base = C.c_void_p()
         check(lib.sq_tp_alloc(C.byref(base), total), "sq_tp_alloc")
         self.base = base.value
@@ -51,8 +58,11 @@ class PeerBuffers:
             self._opened.append(p.value)
         arr = C.c_void_p * 8
         self.proj_ptrs = [arr(*[(b + w * part) for b in self.bases] + [None] * (8 - self.N)) for w in range(2)]
-        self.flag_ptrs = arr(*[(b + 2 * part) for b in self.bases] + [None] * (8 - self.N))
-        self.epoch_ptr = self.base + 2 * part + self.FLAG_BYTES
+        self.red_ptrs = [arr(*[(b + (2 + w) * part) for b in self.bases] + [None] * (8 - self.N)) for w in range(2)]
+        self.flag_ptrs = arr(*[(b + 4 * part) for b in self.bases] + [None] * (8 - self.N))
+        self.epoch_ptr = self.base + 4 * part + self.FLAG_BYTES
+        rf0 = 4 * part + 2 * self.FLAG_BYTES
+        self.rowflag_ptrs = [arr(*[(b + rf0 + w * rowflag_bytes) for b in self.bases] + [None] * (8 - self.N)) for w in range(2)]
         self.buf = [torch.as_tensor(_CudaArray(self.base + w * part, (n_max, hidden)), device=self.device) for w in range(2)]
         assert self.buf[0].data_ptr() == self.base and self.buf[0].dtype == torch.float16
         dist.barrier(group=group)                      # every rank has mapped every peer before the first kernel runs
@@ -60,6 +70,12 @@ class PeerBuffers:
     def allreduce_add_rmsnorm(self, which: int, resid: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, n: int,
                               eps: float):
         """resid += sum over ranks of partial buffer `which`; out = rmsnorm(resid) * weight  (one kernel per rank)."""
+        if self.two_shot:
+            check(_lib.load().sq_tp_allreduce2_add_rmsnorm(ptr(resid), self.proj_ptrs[which], self.red_ptrs[which],
+                                                           self.flag_ptrs, self.rowflag_ptrs[which], self.epoch_ptr,
+                                                           self.rank, self.N, ptr(weight), ptr(out), n, self.hidden, eps,
+                                                           stream_ptr()), "sq_tp_allreduce2_add_rmsnorm")
+            return
         check(_lib.load().sq_tp_allreduce_add_rmsnorm(ptr(resid), self.proj_ptrs[which], self.flag_ptrs, self.epoch_ptr,
                                                       self.rank, self.N, ptr(weight), ptr(out), n, self.hidden, eps,
                                                       stream_ptr()), "sq_tp_allreduce_add_rmsnorm")

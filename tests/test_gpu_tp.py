@@ -90,9 +90,12 @@ def _worker(rank, world, port, q, variant="tiny"):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("variant", ["tiny", "70b-8l"])
-def test_tp2_decode_matches_single_gpu(variant):
+@pytest.mark.parametrize("variant,shot", [("tiny", "1"), ("tiny", "2"), ("70b-8l", "2")])
+def test_tp2_decode_matches_single_gpu(variant, shot):
+    """shot = fused all-reduce flavour (csrc/sq_tp.cu): 1 = one-shot pull (default below 4 ranks), 2 = two-shot
+    reduce-scatter + all-gather in one kernel (default from 4 ranks up) -- both must work at any N."""
     import torch.multiprocessing as mp
+    os.environ["SQ_TP_SHOT"] = shot                   # inherited by the spawned ranks
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -107,7 +110,7 @@ def test_tp2_decode_matches_single_gpu(variant):
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, "tp_parity_test.log"), "a") as f:
-        f.write(f"{variant}: peer_error={err} " + " ".join(f"[iter {it} same={same} rel={rel:.3e}]" for it, same, rel in res) + "\n")
+        f.write(f"{variant} shot={shot}: peer_error={err} " + " ".join(f"[iter {it} same={same} rel={rel:.3e}]" for it, same, rel in res) + "\n")
     # logits are comparable while both runs hold the same token tree (up to and including the first differing iteration)
     for it, same, rel in res:
         assert rel < 2e-3, f"iter {it}: TP-2 target logits differ from TP-1 by {rel} (relative to max |logit|)"

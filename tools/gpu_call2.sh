@@ -21,3 +21,6 @@ for f in "qkv:128,1,2" "qkv:192,1,2" "qkv:96,1,1" "gate_up:256,1,2" "gate_up:160
 done
 SQ_PDL=1 timeout 300 python tools/gemm_probe.py > gpurun_out/r2b_gemm_pdl.log 2>&1
 cat gpurun_out/r2b_gemm_default.log gpurun_out/r2b_gemm_forced.log gpurun_out/r2b_gemm_pdl.log | cut -c1-230
+# the reference's own tests/testbed.py, verbatim, on the drop-in modules (c2 shapes, bundled openwebtext prompts)
+timeout 600 python tools/run_reference_testbed.py -- --model random-init:llama-68m:1 --target random-init:llama-2-7b:2 --growmap $PWD/A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt --T 0.6 --P 1.0 --M 384 --dataset openwebtext --start 0 --end 20 --Mode greedy > gpurun_out/r2b_ref_testbed_verbatim.log 2>&1; echo "verbatim testbed rc=$?"
+tail -4 gpurun_out/r2b_ref_testbed_verbatim.log

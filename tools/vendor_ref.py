@@ -3,7 +3,8 @@
 
 The reference is pure Python with no build system (no setup.py / pyproject.toml => `pip install --target baseline/_ref
 /root/reference` cannot work), so the recipe copies the modules of the hot path -- Engine/*.py, Tree/*.py, utils.py --
-byte for byte from /root/reference into the git-ignored `oracle/_ref/` (it travels with gpurun snapshots exactly like a
+(plus the tests/testbed*.py drivers and the bundled pre-tokenised openwebtext_eval prompts) byte for byte from
+/root/reference into the git-ignored `oracle/_ref/` (it travels with gpurun snapshots exactly like a
 built .so; it is never committed) and writes a manifest of sha256 sums.  `__graft_entry__.build()` runs it whenever
 /root/reference is present; on the GPU box the prebuilt copy is used as is.
 
@@ -19,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference"
 DST = os.path.join(ROOT, "oracle", "_ref")
 PARTS = ("Engine", "Tree")
-FILES = ("utils.py",)
+FILES = ("utils.py", "tests/testbed.py", "tests/testbed_greedy.py")      # the drivers run VERBATIM by tools/run_reference_testbed.py
+DATA = ("dataset/openwebtext_eval",)                                     # bundled pre-tokenised prompts (no tokenizer / hub)
 
 
 def vendor(src: str = SRC, dst: str = DST) -> bool:
@@ -34,8 +36,13 @@ def vendor(src: str = SRC, dst: str = DST) -> bool:
                 shutil.copyfile(os.path.join(src, part, f), os.path.join(dst, part, f))
                 manifest[f"{part}/{f}"] = None
     for f in FILES:
+        os.makedirs(os.path.dirname(os.path.join(dst, f)), exist_ok=True)
         shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
         manifest[f] = None
+    for d in DATA:
+        if os.path.isdir(os.path.join(dst, d)):
+            shutil.rmtree(os.path.join(dst, d))
+        shutil.copytree(os.path.join(src, d), os.path.join(dst, d))
     for rel in manifest:
         with open(os.path.join(dst, rel), "rb") as fh:
             manifest[rel] = hashlib.sha256(fh.read()).hexdigest()
