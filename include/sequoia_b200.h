@@ -149,6 +149,11 @@ int sq_sample_replace(const sq_half* logits, int64_t ld_logits, const int64_t* w
 /* get_residual (utils.py:5-8): out = relu(p-q) / sum(relu(p-q)), fp16 roundings as torch. */
 int sq_residual(const sq_half* p, const sq_half* q, sq_half* out, int V, void* stream);
 
+/* get_sampling_logits (utils.py:65-77), in place on n rows: tokens whose predecessor in descending-logit order has
+ * cumulative probability fp16(cumsum(softmax(fp16(logits/T)))) > fp16(top_p) are set to -inf; equal logits rank by
+ * ascending index.  No-op when top_p >= 1. */
+int sq_top_p_filter(sq_half* logits, int64_t ld, int n, int V, float top_p, float T, void* stream);
+
 /* argmax over V per row -> int64 (GreedyTree.py:186). */
 int sq_argmax_rows(const sq_half* logits, int64_t ld, int n, int V, int64_t* out, void* stream);
 

@@ -302,13 +302,17 @@ class LlamaOracle:
     mode "TG" = target engine (explicit attention over kv_len slots)."""
 
     def __init__(self, cfg: LlamaCfg, weights: Dict[str, torch.Tensor], max_length: int, mode: str,
-                 dtype=torch.float16):
+                 dtype=torch.float16, device="cpu"):
         assert mode in ("FI", "TG")
         self.cfg, self.w, self.max_length, self.mode, self.dtype = cfg, weights, max_length, mode, dtype
         self.kv_cache = KVCacheOracle(cfg.num_hidden_layers, cfg.num_key_value_heads, cfg.head_dim,
                                       max_length, dtype)
         self.cos, self.sin = rope_cache(cfg.head_dim, max_length, cfg.rope_theta,
                                         cfg.max_position_embeddings, dtype)
+        if str(device) != "cpu":      # tests only: the same torch op sequence on the reference's own device (weights given there)
+            self.kv_cache.k_cache = self.kv_cache.k_cache.to(device)
+            self.kv_cache.v_cache = self.kv_cache.v_cache.to(device)
+            self.cos, self.sin = self.cos.to(device), self.sin.to(device)
 
     @torch.no_grad()
     def forward(self, input_ids, storage_ids, position_ids, attention_mask) -> torch.Tensor:

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "sq_sample_replace": (i32, [vp, i64, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp]),
     "sq_residual": (i32, [vp, vp, vp, i32, vp]),
     "sq_argmax_rows": (i32, [vp, i64, i32, i32, vp, vp]),
+    "sq_top_p_filter": (i32, [vp, i64, i32, i32, f32, f32, vp]),
     "sq_accept_stochastic": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, i32, i32, vp]),
     "sq_accept_greedy": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]),
     "sq_l2_prefetch": (i32, [vp, i64, i32, i64, i64, vp]),

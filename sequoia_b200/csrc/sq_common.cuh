@@ -29,6 +29,28 @@ void count_launch(int n);
     sq::count_launch(1);                                                        \
   } while (0)
 
+// Programmatic dependent launch (SQ_PDL=1): kernel N+1 is scheduled while kernel N drains; every kernel launched this
+// way executes pdl_wait() FIRST (before any global access and before any early return), so completion stays transitive
+// along the stream (N+1 cannot finish before N has finished and flushed), then pdl_trigger() to let N+2 be scheduled.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Device-side decode state (int32 words), owned by the Tree object, read by every kernel
 // that needs the dynamic prefix length so that whole iterations are CUDA-graph static.
 enum StateWord : int {

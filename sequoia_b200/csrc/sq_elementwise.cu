@@ -8,6 +8,8 @@ namespace sq {
 // ---------------------------------------------------------------------------------------------
 __global__ void embed_rows_kernel(const __half* __restrict__ table, const int64_t* __restrict__ tokens,
                                   const int32_t* __restrict__ state, int n0, int hidden, __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x;
   const int base = row_base(state, n0);
   const int64_t tok = tokens[base + r];
@@ -26,6 +28,16 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(__half* __restrict__ resid
   const int r = blockIdx.x;
   const int nvec = hidden / 8;
   Pack8 v[MAXV];
+  Pack8 wv[MAXV];
+  if (out != nullptr) {                       // the norm weight does not depend on the previous kernel
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = threadIdx.x + i * 256;
+      if (c < nvec) wv[i].u = reinterpret_cast<const uint4*>(w)[c];
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
@@ -52,12 +64,11 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(__half* __restrict__ resid
   for (int i = 0; i < MAXV; ++i) {
     const int c = threadIdx.x + i * 256;
     if (c < nvec) {
-      Pack8 wv, o;
-      wv.u = reinterpret_cast<const uint4*>(w)[c];
+      Pack8 o;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const __half xn = f2h(h2f(v[i].h[j]) * inv);        // hidden_states.to(input_dtype)
-        o.h[j] = f2h(h2f(wv.h[j]) * h2f(xn));               // weight * x  (fp16 mul)
+        o.h[j] = f2h(h2f(wv[i].h[j]) * h2f(xn));            // weight * x  (fp16 mul)
       }
       reinterpret_cast<uint4*>(out + (int64_t)r * hidden)[c] = o.u;
     }
@@ -66,6 +77,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(__half* __restrict__ resid
 
 // ---------------------------------------------------------------------------------------------
 __global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restrict__ out, int n, int inter) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t nvec = (int64_t)n * (inter / 8);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (inter / 8);
@@ -90,8 +103,10 @@ __global__ void __launch_bounds__(256) rope_kv_append_kernel(
     __half* __restrict__ qkv, int ld, int H, int Hkv, int D, const __half* __restrict__ cosc,
     const __half* __restrict__ sinc, const int64_t* __restrict__ position_ids, const int64_t* __restrict__ storage_ids,
     const int32_t* __restrict__ state, int n0, __half* __restrict__ k_layer, __half* __restrict__ v_layer, int M) {
-  // let a programmatically dependent attention launch start its prologue (it waits for this grid's completion itself)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // under programmatic dependent launch: wait for the qkv GEMM, then let the attention launch start its prologue (it
+  // waits for this grid's completion itself)
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x;
   const int base = row_base(state, n0);
   const int64_t pos = position_ids[base + r];
@@ -134,7 +149,7 @@ extern "C" int sq_embed_rows(const sq_half* table, const int64_t* tokens, const 
                              int hidden, sq_half* out, void* stream) {
   SQ_CHECK_ARG(hidden % 8 == 0 && n >= 0, "sq_embed_rows: hidden %% 8 != 0");
   if (n == 0) return SQ_OK;
-  embed_rows_kernel<<<n, 128, 0, (cudaStream_t)stream>>>((const __half*)table, tokens, state, n0, hidden, (__half*)out);
+  launch_k(embed_rows_kernel, dim3(n), dim3(128), 0, (cudaStream_t)stream, (const __half*)table, tokens, state, n0, hidden, (__half*)out);
   SQ_CHECK_LAUNCH("sq_embed_rows");
   return SQ_OK;
 }
@@ -145,10 +160,10 @@ static int launch_rmsnorm(__half* resid, const __half* delta, const __half* x, c
   SQ_CHECK_ARG(hidden % 8 == 0 && hidden <= 256 * 8 * 8, "sq_rmsnorm: hidden=%d unsupported", hidden);
   if (n == 0) return SQ_OK;
   const int nvec = hidden / 8;
-  if (nvec <= 256) rmsnorm_kernel<1, ADD><<<n, 256, 0, st>>>(resid, delta, x, w, out, hidden, eps);
-  else if (nvec <= 512) rmsnorm_kernel<2, ADD><<<n, 256, 0, st>>>(resid, delta, x, w, out, hidden, eps);
-  else if (nvec <= 1024) rmsnorm_kernel<4, ADD><<<n, 256, 0, st>>>(resid, delta, x, w, out, hidden, eps);
-  else rmsnorm_kernel<8, ADD><<<n, 256, 0, st>>>(resid, delta, x, w, out, hidden, eps);
+  if (nvec <= 256) launch_k(rmsnorm_kernel<1, ADD>, dim3(n), dim3(256), 0, st, resid, delta, x, w, out, hidden, eps);
+  else if (nvec <= 512) launch_k(rmsnorm_kernel<2, ADD>, dim3(n), dim3(256), 0, st, resid, delta, x, w, out, hidden, eps);
+  else if (nvec <= 1024) launch_k(rmsnorm_kernel<4, ADD>, dim3(n), dim3(256), 0, st, resid, delta, x, w, out, hidden, eps);
+  else launch_k(rmsnorm_kernel<8, ADD>, dim3(n), dim3(256), 0, st, resid, delta, x, w, out, hidden, eps);
   SQ_CHECK_LAUNCH("sq_rmsnorm");
   return SQ_OK;
 }
@@ -171,7 +186,7 @@ extern "C" int sq_silu_mul(const sq_half* gate_up, sq_half* out, int n, int inte
   const int64_t nvec = (int64_t)n * (inter / 8);
   int blocks = (int)((nvec + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  silu_mul_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)gate_up, (__half*)out, n, inter);
+  launch_k(silu_mul_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const __half*)gate_up, (__half*)out, n, inter);
   SQ_CHECK_LAUNCH("sq_silu_mul");
   return SQ_OK;
 }
@@ -181,9 +196,9 @@ extern "C" int sq_rope_kv_append(sq_half* qkv, int ld, int H, int Hkv, int D, co
                                  int n, sq_half* k_layer, sq_half* v_layer, int M, void* stream) {
   SQ_CHECK_ARG(D % 16 == 0 && ld % 8 == 0, "sq_rope_kv_append: head dim %d / pitch %d must be multiples of 16 / 8", D, ld);
   if (n == 0) return SQ_OK;
-  rope_kv_append_kernel<<<n, 256, 0, (cudaStream_t)stream>>>((__half*)qkv, ld, H, Hkv, D, (const __half*)cos,
-                                                                 (const __half*)sin, position_ids, storage_ids, state,
-                                                                 n0, (__half*)k_layer, (__half*)v_layer, M);
+  launch_k(rope_kv_append_kernel, dim3(n), dim3(256), 0, (cudaStream_t)stream, (__half*)qkv, ld, H, Hkv, D,
+           (const __half*)cos, (const __half*)sin, position_ids, storage_ids, state, n0, (__half*)k_layer,
+           (__half*)v_layer, M);
   SQ_CHECK_LAUNCH("sq_rope_kv_append");
   return SQ_OK;
 }

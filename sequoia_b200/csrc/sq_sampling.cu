@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(NT) sample_level_kernel(
   __shared__ float red[NW];
   __shared__ uint32_t redu[NW];
   const int j = blockIdx.x;
+  const int nb = n_branch ? n_branch[j] : 0;
+  const int k_need = positions ? k_max : min(nb, k_max);   // children this row actually needs (block-uniform)
+  if (k_need == 0) return;
   const int prow = parent_rows ? parent_rows[j] : j;
   const int nvec = V / 8;
   uint32_t key[CH * 8];
@@ -129,13 +132,54 @@ __global__ void __launch_bounds__(NT) sample_level_kernel(
       }
     }
   }
-  // k rounds of block-wide arg-max over unique (score, index) keys; ties on the score resolve to the lower index
+  // top-k over unique (score, index) keys; ties on the score resolve to the lower index
   uint32_t best = 0u;
 #pragma unroll
   for (int e = 0; e < CH * 8; ++e) best = max(best, key[e]);
-  const int nb = n_branch ? n_branch[j] : 0;
   const int base = tokens ? row_base(state, child_first[j]) : 0;
-  for (int rnd = 0; rnd < k_max; ++rnd) {
+  // Fast path (k <= 32): the k-th largest of the 32 warp maxima is a lower bound of the k-th largest key (at least k keys
+  // reach it), and usually only a few more do: collect the keys >= that threshold in shared memory and rank them directly
+  // (rank = number of larger candidates) -- three block barriers instead of two per selected child.
+  if (k_need <= 32) {
+    __shared__ uint32_t cand[NT];
+    __shared__ int cnt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, best);
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();                       // (also orders the last read of `redu`/`red` by scale_and_stats)
+    if (lane == 0) redu[warp] = wmax;
+    __syncthreads();
+    uint32_t v = redu[lane], thr = 0u;     // NW == 32
+    for (int r = 0; r < k_need; ++r) {
+      thr = __reduce_max_sync(0xffffffffu, v);
+      if (v == thr) v = 0u;
+    }
+    if (best >= thr && best != 0u) {       // (valid keys are never 0; thr == 0 only when few warps hold valid keys)
+#pragma unroll
+      for (int e = 0; e < CH * 8; ++e)
+        if (key[e] >= thr && key[e] != 0u) {
+          const int p = atomicAdd(&cnt, 1);
+          if (p < NT) cand[p] = key[e];
+        }
+    }
+    __syncthreads();
+    const int C = cnt;
+    if (C <= NT) {
+      if ((int)threadIdx.x < C) {
+        const uint32_t mine = cand[threadIdx.x];
+        int rank = 0;
+        for (int i = 0; i < C; ++i) rank += (cand[i] > mine) ? 1 : 0;
+        if (rank < k_need) {
+          const int64_t idx = (int64_t)(0xFFFFu - (mine & 0xFFFFu));
+          if (positions) positions[(int64_t)j * k_max + rank] = idx;
+          if (tokens && rank < nb) tokens[base + rank] = idx;
+        }
+      }
+      return;
+    }
+    // (more than NT keys reach the threshold -- e.g. an index-sorted row in top-k mode: fall through to the round loop)
+  }
+  for (int rnd = 0; rnd < k_need; ++rnd) {
     const uint32_t top = block_max_u32(best, redu);
     if (best == top) {                    // unique owner (keys embed the index)
       const int64_t idx = (int64_t)(0xFFFFu - (top & 0xFFFFu));
@@ -289,6 +333,155 @@ __global__ void __launch_bounds__(NT) argmax_rows_kernel(const __half* __restric
   if (threadIdx.x == 0) out[blockIdx.x] = (int64_t)(0xFFFFu - (top & 0xFFFFu));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// get_sampling_logits (utils.py:65-77): nucleus (top-p) filter, in place.  The reference sorts the row, takes
+// cumsum(softmax(sorted / T)) in fp16 and removes every token whose PREDECESSOR's cumulative probability exceeds top_p
+// (the first sorted token is always kept).  No sort here: the fp16 probabilities are integer multiples of 2^-24, so
+// "mass of all tokens ranked before token i" is an exact integer S(i) that a two-level histogram over the 16-bit
+// order-preserving key of fp16(logit / T) yields directly (high byte, then low byte inside the boundary bin; per-warp
+// private histograms, integer atomics => order-independent, deterministic).  Token i is removed iff
+// fp16(S(i) * 2^-24) > fp16(top_p) -- the comparison torch performs.  Tokens with the SAME fp16 logit tie: they are
+// ranked by ascending index (a stable descending sort), resolved with a block scan over the boundary key only.
+// (torch's cumsum adds the same fp16 terms in fp32 in scan order; the exact sum differs from it by < 2^-20 relative, far
+// below the fp16 rounding of the comparison.)
+__device__ __forceinline__ bool topp_pred(uint32_t S, float tp) { return h2f(f2h((float)S * (1.0f / 16777216.f))) > tp; }
+
+__global__ void __launch_bounds__(NT) top_p_filter_kernel(__half* __restrict__ logits, int64_t ld, int V, float inv_T,
+                                                           float tp) {
+  __shared__ float red[NW];
+  __shared__ uint32_t whist[NW][256];
+  __shared__ uint32_t hist[256];
+  __shared__ int sel[2];            // boundary bin, mass ranked before it
+  __shared__ uint32_t wtot[CH][NW];
+  __half* row = logits + blockIdx.x * ld;
+  const int nvec = V / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Pack8 xt[CH];
+  load_row(row, V, xt);
+  float mx, sum;
+  scale_and_stats(xt, inv_T, red, mx, sum);
+  uint32_t before = 0u;             // mass ranked before the current boundary bin
+  int hi = -1, key_b = -1;
+  for (int level = 0; level < 2; ++level) {
+    for (int i = threadIdx.x; i < NW * 256; i += NT) (&whist[0][0])[i] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t k = ord16(xt[i].h[e]);
+        const uint32_t w = (uint32_t)(h2f(softmax_val(xt[i].h[e], mx, 0.f, sum)) * 16777216.f);
+        if (w != 0u && (level == 0 || (int)(k >> 8) == hi)) atomicAdd(&whist[warp][level == 0 ? (k >> 8) : (k & 255u)], w);
+      }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      uint32_t t = 0u;
+#pragma unroll 8
+      for (int w = 0; w < NW; ++w) t += whist[w][threadIdx.x];
+      hist[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) sel[0] = -1;
+    __syncthreads();
+    if (warp == 0) {
+      // lane l owns bins 255-8l .. 248-8l (descending order of value); exclusive scan over the lanes
+      uint32_t m[8], tot = 0u;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { m[b] = hist[255 - 8 * lane - b]; tot += m[b]; }
+      uint32_t inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      uint32_t a = before + inc - tot;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (!topp_pred(a, tp) && topp_pred(a + m[b], tp)) { sel[0] = 255 - 8 * lane - b; sel[1] = (int)a; }   // unique
+        a += m[b];
+      }
+    }
+    __syncthreads();
+    const int bb = sel[0];
+    if (bb < 0) return;             // the whole row stays below top_p: nothing to remove (block-uniform)
+    before = (uint32_t)sel[1];
+    if (level == 0) hi = bb; else key_b = (hi << 8) | bb;
+    __syncthreads();
+  }
+  // ties on the boundary key: the first t_keep of them (ascending index) stay
+  uint32_t w_b = 0u;
+  int cs[CH], excl[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    cs[i] = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if ((int)ord16(xt[i].h[e]) == key_b) {
+        ++cs[i];
+        w_b = (uint32_t)(h2f(softmax_val(xt[i].h[e], mx, 0.f, sum)) * 16777216.f);
+      }
+  }
+  w_b = __reduce_max_sync(0xffffffffu, w_b);
+  if (lane == 0) red[warp] = __uint_as_float(w_b);
+  int inc[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    int v = cs[i];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    inc[i] = v;
+    if (lane == 31) wtot[i][warp] = (uint32_t)v;
+  }
+  __syncthreads();
+  w_b = __reduce_max_sync(0xffffffffu, __float_as_uint(red[lane]));          // NW == 32: every warp gets the bin's weight
+  int total = 0;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    int v = (int)wtot[i][lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    const int prev = __shfl_sync(0xffffffffu, v, (warp + 31) & 31);
+    excl[i] = total + (warp ? prev : 0) + inc[i] - cs[i];
+    total += __shfl_sync(0xffffffffu, v, 31);
+  }
+  // smallest t with pred(before + t * w_b): tie ranks >= t are removed (pred(before) is false, pred at t = total true)
+  int lo = 0, hi_t = total;
+  while (lo < hi_t) {
+    const int mid = (lo + hi_t) >> 1;
+    if (topp_pred(before + (uint32_t)mid * w_b, tp)) hi_t = mid; else lo = mid + 1;
+  }
+  const int t_keep = lo;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = i * NT + threadIdx.x;
+    if (c >= nvec) continue;
+    bool any = false;
+    bool rm[8];
+    int rank = excl[i];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = (int)ord16(xt[i].h[e]);
+      rm[e] = (k < key_b) || (k == key_b && rank >= t_keep);
+      if (k == key_b) ++rank;
+      any |= rm[e];
+    }
+    if (any) {
+      Pack8 x;
+      x.u = reinterpret_cast<const uint4*>(row)[c];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (rm[e]) x.h[e] = __ushort_as_half((unsigned short)0xFC00u);     // -inf
+      reinterpret_cast<uint4*>(row)[c] = x.u;
+    }
+  }
+}
+
 }  // namespace sq
 
 using namespace sq;
@@ -349,5 +542,14 @@ extern "C" int sq_argmax_rows(const sq_half* logits, int64_t ld, int n, int V, i
   if (n == 0) return SQ_OK;
   argmax_rows_kernel<<<n, NT, 0, (cudaStream_t)stream>>>((const __half*)logits, ld, V, out);
   SQ_CHECK_LAUNCH("sq_argmax_rows");
+  return SQ_OK;
+}
+
+extern "C" int sq_top_p_filter(sq_half* logits, int64_t ld, int n, int V, float top_p, float T, void* stream) {
+  SQ_CHECK_V(V);
+  if (n == 0 || top_p >= 1.0f) return SQ_OK;                       // utils.py:68: only when top_p < 1
+  const float tp = __half2float(__float2half_rn(top_p));           // torch compares in the tensor's dtype (fp16)
+  top_p_filter_kernel<<<n, NT, 0, (cudaStream_t)stream>>>((__half*)logits, ld, V, 1.0f / T, tp);
+  SQ_CHECK_LAUNCH("sq_top_p_filter");
   return SQ_OK;
 }

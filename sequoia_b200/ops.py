@@ -142,6 +142,15 @@ def residual(p, q, out=None):
     return out
 
 
+def top_p_filter_(logits, top_p: float, T: float):
+    """get_sampling_logits (utils.py:65-77), in place on (n, V) fp16 logits."""
+    _need(logits, F16, "top_p_filter_")
+    n, V = logits.shape
+    check(_lib.load().sq_top_p_filter(ptr(logits), logits.stride(0), n, V, float(top_p), float(T), stream_ptr()),
+          "sq_top_p_filter")
+    return logits
+
+
 def argmax_rows(logits, out=None):
     n, V = logits.shape
     if out is None:

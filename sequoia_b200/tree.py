@@ -195,7 +195,7 @@ class _Runtime:
         if self.greedy:
             if self.policy == "greedys":                                                # GreedySTree.py:188-190
                 if self.top_p < 1.0:
-                    _top_p_filter_(self.target_logits, self.top_p, self.T)
+                    ops.top_p_filter_(self.target_logits, self.top_p, self.T)
                 if self.external_tuniform is None:
                     self.tuniform.uniform_()
                 # softmax(l/T).multinomial(1) per row == the k=1 exponential race of sampling_without_replacement
@@ -206,7 +206,7 @@ class _Runtime:
                               self.accept_idx, self.state, self.max_target_seq)
         else:
             if self.top_p < 1.0:                                                        # utils.py:65-77 (off at P=1)
-                _top_p_filter_(self.target_logits, self.top_p, self.T)
+                ops.top_p_filter_(self.target_logits, self.top_p, self.T)
             if self.external_noise is None:
                 self.noise.exponential_(1.0)                                            # torch.multinomial's draw
             ops.accept_stochastic(self.target_logits, self.draft_logits, self.r, self.noise, st.succ_off, st.succ,
@@ -296,7 +296,8 @@ class _Runtime:
 
 
 def _top_p_filter_(logits: torch.Tensor, top_p: float, T: float):
-    """get_sampling_logits (utils.py:65-77), in place; torch ops (not on any named configuration's path)."""
+    """get_sampling_logits (utils.py:65-77) restated with torch ops -- NOT on the product path (that is the
+    `sq_top_p_filter` kernel, ops.top_p_filter_); kept as the on-device cross-check of tests/test_gpu_kernels.py."""
     sorted_logits, sorted_indices = torch.sort(logits, descending=True)
     cumulative_probs = torch.cumsum(torch.softmax(sorted_logits / T, dim=-1), dim=-1)
     filt = cumulative_probs > top_p

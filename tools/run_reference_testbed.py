@@ -9,7 +9,8 @@ offline GPU box cannot provide is supplied from outside the driver, without touc
   * the Llama-2 tokenizer needs the HF hub   -> AutoTokenizer.from_pretrained returns a tiny local tokenizer; with
                                                 `--dataset openwebtext` the driver only uses it to PAD the bundled,
                                                 already tokenised prompts (dataset/openwebtext_eval of the reference);
-  * weights                                   -> `--model / --target random-init:<name>[:seed]` (engine feature).
+  * weights                                   -> `--model / --target random-init:<name>[:seed]` (engine feature);
+  * this image's `datasets` expects a newer torchvision (`torchvision.io.VideoReader`) -> a placeholder attribute.
 
     python tools/run_reference_testbed.py [--driver testbed.py] -- --model random-init:llama-68m:1 \
         --target random-init:llama-2-7b:2 --growmap <abs path> --T 0.6 --P 1.0 --M 384 --dataset openwebtext --start 0 --end 20
@@ -54,6 +55,12 @@ def main():
         return PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="<unk>", bos_token="<s>", eos_token="</s>")
 
     AutoTokenizer.from_pretrained = staticmethod(local_tokenizer)
+    try:                                     # this image's `datasets` torch formatter imports a class its torchvision lacks
+        import torchvision.io as tvio
+        if not hasattr(tvio, "VideoReader"):
+            tvio.VideoReader = type("VideoReader", (), {})
+    except Exception:
+        pass
     sys.path.insert(0, ROOT)                 # Engine / Tree / utils / data_converter = this repository's drop-ins
     os.chdir(REF_TESTS)                      # the driver's relative paths ("..", "../dataset/openwebtext_eval")
     sys.argv = [path] + argv
