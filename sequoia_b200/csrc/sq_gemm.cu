@@ -2,9 +2,10 @@
 // in tensor memory, fp16 out) -- nn.Linear of the target / draft forward (Engine/Llama_modules.py:108-110,138,270-272,
 // Llama_model.py:213) for at most 128 rows.  With 128 rows every weight byte is used once: the kernel is a pure HBM
 // stream (roofline = weight bytes / HBM bandwidth), so the design goal is bytes in flight, not FLOPs:
-//   * one CTA per 128- or 256-wide slice of N (one wave on 148 SMs), warp-specialised: 1 TMA producer lane, 1 MMA
-//     issuer lane, 4 epilogue warps; a 4-6 stage mbarrier ring of (A 128x64, W BNx64) SWIZZLE_128B tiles keeps
-//     128-192 KB per SM in flight; tcgen05.mma kind::f16 M=128 N=BN K=16, accumulator in TMEM;
+//   * one CTA per BN-wide slice of N (one wave on 148 SMs), warp-specialised: a weight-TMA lane, an activation-TMA
+//     lane, an MMA issuer lane, 4 epilogue warps; TWO mbarrier rings of SWIZZLE_128B tiles -- 10-20 weight stages
+//     (BN x 64, 156-168 KB of HBM bytes in flight per SM) and 3-4 activation stages (128 x 64, from L2);
+//     tcgen05.mma kind::f16 M=128 N=BN K=16, accumulator in TMEM;
 //   * narrow outputs (o_proj / down_proj: N = hidden = 32 slices only) are split along K over a thread-block cluster
 //     (1, SPLIT, 1): each CTA streams 1/SPLIT of K, pushes its fp32 partial rows into the shared memory of the row's
 //     owner CTA (st.shared::cluster), one cluster barrier, owners add in a fixed order and store fp16.
@@ -30,20 +31,37 @@ struct GemmArgs {
 };
 
 constexpr int G_BK = 64;
-constexpr int G_THREADS = 192;       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int G_THREADS = 224;       // warp 0: weight TMA, warp 1: MMA + TMEM alloc, warp 2: activation TMA, warps 3..6: epilogue
 
 __host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
-template <int BN, int STAGES, int SPLIT>
+// Two INDEPENDENT rings.  What bounds a 128-row weight stream is the number of HBM bytes each SM keeps in flight
+// (Little: ~6.5 TB/s x ~2 us loaded latency = 13 MB over 148 SMs = ~90 KB per SM of WEIGHT bytes); the activation
+// slab comes from L2 (short latency, re-read by every CTA) and needs only a few stages.  With one coupled ring every
+// stage carries a 16 KB activation tile, i.e. half of the shared memory holds L2-resident data (ncu, round 2: 72 KB of
+// weight bytes in flight per CTA at BN=96 vs 124 KB in cuBLASLt's 2-CTA kernel).  Here: SA (3-4) activation stages and
+// as many weight stages as the rest of the 227 KB holds (156-168 KB).
+__host__ __device__ constexpr int gemm_sa(int bn) { return bn >= 192 ? 3 : 4; }
+__host__ __device__ constexpr int gemm_wpad(int bn) { return ((bn * 128 + 1023) / 1024) * 1024; }
+__host__ __device__ constexpr int gemm_sw(int bn) { return (220 * 1024 - gemm_sa(bn) * 16384) / gemm_wpad(bn); }
+
+template <int BN, int SPLIT>
 struct GemmSmem {
+  static constexpr int SA = gemm_sa(BN), SW = gemm_sw(BN);
   static constexpr int A_BYTES = 128 * 128;            // 128 rows x 64 halfs
   static constexpr int W_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + ((W_BYTES + 1023) / 1024) * 1024;   // stages stay 1024 B aligned (SW128)
-  static constexpr int OFF_BAR = STAGES * STAGE_BYTES; // full[STAGES], empty[STAGES], tmem_full, tmem ptr
-  static constexpr int OFF_RED = OFF_BAR + 256;        // split-K: SPLIT slots x (128/SPLIT rows) x (BN+4) floats
+  static constexpr int W_PAD = gemm_wpad(BN);          // stages stay 1024 B aligned (SW128)
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_A = SW * W_PAD;
+  static constexpr int OFF_BAR = OFF_A + SA * A_BYTES; // full_w[SW], empty_w[SW], full_a[SA], empty_a[SA], tmem_full, tmem ptr
+  static constexpr int BAR_BYTES = 512;
+  static_assert((2 * SW + 2 * SA + 2) * 8 <= BAR_BYTES, "barrier block");
+  // split-K: SPLIT slots x (128/SPLIT rows) x (BN+4) floats, ALIASED onto the weight ring (dead once every CTA of the
+  // cluster has retired its MMAs: a cluster barrier separates the main loops from the pushes)
   static constexpr int R_STRIDE = BN + 4;
   static constexpr int RED_BYTES = SPLIT > 1 ? 128 * R_STRIDE * 4 : 0;
-  static constexpr int TOTAL = OFF_RED + RED_BYTES;
+  static_assert(RED_BYTES <= SW * W_PAD, "reduction buffers must fit the weight ring");
+  static constexpr int TOTAL = OFF_BAR + BAR_BYTES;
 };
 
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
@@ -56,14 +74,18 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // MC = CTAs (along N) that share one activation K-slab: each loads 128/MC of its rows and multicasts them to all.
-template <int BN, int STAGES, int SPLIT, int MC>
+template <int BN, int SPLIT, int MC>
 __global__ void __launch_bounds__(G_THREADS, 1)
     gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, GemmArgs g) {
   // cluster (MC, SPLIT): rank = mcr + MC * ks.  CTAs with the same ks share the activation slab (multicast group); CTAs
   // with the same mcr hold the K-splits of one output tile (DSMEM reduction group).
-  using SM = GemmSmem<BN, STAGES, SPLIT>;
+  using SM = GemmSmem<BN, SPLIT>;
+  constexpr int SW = SM::SW, SA = SM::SA;
   constexpr int TCOLS = tmem_cols_for(BN);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -74,14 +96,22 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   const int kb0 = ks * g.kb_per_split;
   const int nkb = g.kb_per_split;
   const uint32_t s_base = ptx::smem_u32(smem);
-  const uint32_t bar_full = s_base + SM::OFF_BAR, bar_empty = bar_full + 8 * STAGES, bar_tmem = bar_empty + 8 * STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + 16 * STAGES + 8);
+  const uint32_t s_w = s_base + SM::OFF_W, s_a = s_base + SM::OFF_A;
+  const uint32_t full_w = s_base + SM::OFF_BAR, empty_w = full_w + 8 * SW, full_a = empty_w + 8 * SW,
+                 empty_a = full_a + 8 * SA, bar_tmem = empty_a + 8 * SA;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + (2 * SW + 2 * SA + 1) * 8);
+  const uint16_t mc_mask = (uint16_t)(((1u << MC) - 1u) << (MC * ks));
 
   if (tid == 0) {
+#pragma unroll 1
+    for (int s = 0; s < SW; ++s) {
+      ptx::mbar_init(full_w + 8 * s, 1);
+      ptx::mbar_init(empty_w + 8 * s, 1);
+    }
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, 1);
-      ptx::mbar_init(bar_empty + 8 * s, MC);               // every CTA that received this slot's A rows must release it
+    for (int s = 0; s < SA; ++s) {
+      ptx::mbar_init(full_a + 8 * s, 1);
+      ptx::mbar_init(empty_a + 8 * s, MC);                 // every CTA that received this slot's rows must release it
     }
     ptx::mbar_init(bar_tmem, 1);
     ptx::fence_barrier_init();
@@ -92,66 +122,74 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (MC > 1)   // the peers' barriers must be initialised before any multicast / remote arrive can target them
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (MC > 1) cluster_sync_all();   // the peers' barriers must be initialised before any multicast / remote arrive targets them
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== weight producer: never waits for the previous kernel (weights are constants), so under programmatic
+    // dependent launch the whole ring fills while that kernel is still draining =====
     if (lane == 0) {
       asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-      // Weights do not depend on the previous kernel: under programmatic dependent launch the first ring of weight
-      // tiles streams in while that kernel is still running; only the activation loads wait for it.
-      const int pre = nkb < STAGES ? nkb : STAGES;
-      for (int kb = 0; kb < pre; ++kb) {
-        const uint32_t sa = s_base + kb * SM::STAGE_BYTES, sw = sa + SM::A_BYTES;
-        ptx::mbar_expect_tx(bar_full + 8 * kb, SM::A_BYTES + SM::W_BYTES);
-        ptx::tma_load_2d(sw, &tm_w, bar_full + 8 * kb, (kb0 + kb) * G_BK, n0);
+      int stage = 0;
+      uint32_t phase = 0;
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (kb >= SW) ptx::mbar_wait_one(empty_w + 8 * stage, phase ^ 1, g.err_flag, 11);
+        ptx::mbar_expect_tx(full_w + 8 * stage, SM::W_BYTES);
+        ptx::tma_load_2d(s_w + stage * SM::W_PAD, &tm_w, full_w + 8 * stage, (kb0 + kb) * G_BK, n0);
+        if (++stage == SW) { stage = 0; phase ^= 1; }
       }
+    }
+  } else if (warp == 2) {
+    // ===== activation producer =====
+    if (lane == 0) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
       int stage = 0;
       uint32_t phase = 0;
+#pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb) {
-        const uint32_t sa = s_base + stage * SM::STAGE_BYTES, sw = sa + SM::A_BYTES;
-        if (kb >= pre) {
-          ptx::mbar_wait_one(bar_empty + 8 * stage, phase ^ 1, g.err_flag, 11);   // slot free in EVERY CTA of the cluster
-          ptx::mbar_expect_tx(bar_full + 8 * stage, SM::A_BYTES + SM::W_BYTES);
-          ptx::tma_load_2d(sw, &tm_w, bar_full + 8 * stage, (kb0 + kb) * G_BK, n0);
-        }
-        if (MC == 1) ptx::tma_load_2d(sa, &tm_a, bar_full + 8 * stage, (kb0 + kb) * G_BK, 0);
-        else tma_load_2d_mc(sa + mcr * (SM::A_BYTES / MC), &tm_a, bar_full + 8 * stage, (kb0 + kb) * G_BK, mcr * (128 / MC),
-                            (uint16_t)(((1u << MC) - 1u) << (MC * ks)));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (kb >= SA) ptx::mbar_wait_one(empty_a + 8 * stage, phase ^ 1, g.err_flag, 14);   // slot free in EVERY CTA of the group
+        ptx::mbar_expect_tx(full_a + 8 * stage, SM::A_BYTES);
+        const uint32_t sa = s_a + stage * SM::A_BYTES;
+        if (MC == 1) ptx::tma_load_2d(sa, &tm_a, full_a + 8 * stage, (kb0 + kb) * G_BK, 0);
+        else tma_load_2d_mc(sa + mcr * (SM::A_BYTES / MC), &tm_a, full_a + 8 * stage, (kb0 + kb) * G_BK, mcr * (128 / MC), mc_mask);
+        if (++stage == SA) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(BN, false);
-      int stage = 0;
-      uint32_t phase = 0;
+      int sw = 0, sa = 0;
+      uint32_t pw = 0, pa = 0;
+#pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb) {
-        ptx::mbar_wait_one(bar_full + 8 * stage, phase, g.err_flag, 12);           // TMA bytes have landed
+        ptx::mbar_wait_one(full_a + 8 * sa, pa, g.err_flag, 12);
+        ptx::mbar_wait_one(full_w + 8 * sw, pw, g.err_flag, 15);
         ptx::tc_fence_after();
-        const uint32_t sa = s_base + stage * SM::STAGE_BYTES, sw = sa + SM::A_BYTES;
+        const uint32_t a_addr = s_a + sa * SM::A_BYTES, w_addr = s_w + sw * SM::W_PAD;
 #pragma unroll
         for (int k = 0; k < G_BK / 16; ++k)
-          ptx::mma_ss(tmem, umma_desc(sa + k * 32, 16, 1024), umma_desc(sw + k * 32, 16, 1024), idesc, (kb | k) != 0);
-        // frees the slot when the MMAs retire -- in every CTA whose multicast writes into this CTA's slot
-        if (MC == 1) ptx::tc_commit(bar_empty + 8 * stage);
-        else tc_commit_mc(bar_empty + 8 * stage, (uint16_t)(((1u << MC) - 1u) << (MC * ks)));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          ptx::mma_ss(tmem, umma_desc(a_addr + k * 32, 16, 1024), umma_desc(w_addr + k * 32, 16, 1024), idesc, (kb | k) != 0);
+        // the slots are free when these MMAs retire -- the activation slot in every CTA that multicasts into it
+        ptx::tc_commit(empty_w + 8 * sw);
+        if (MC == 1) ptx::tc_commit(empty_a + 8 * sa);
+        else tc_commit_mc(empty_a + 8 * sa, mc_mask);
+        if (++sw == SW) { sw = 0; pw ^= 1; }
+        if (++sa == SA) { sa = 0; pa ^= 1; }
       }
       ptx::tc_commit(bar_tmem);                                                    // accumulator complete
     }
-  } else {
+  }
+  const bool epi = warp >= 3;
+  const int lg = warp & 3;                                  // TMEM lane group this warp may access
+  const int row = lg * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
+  if (epi) {
     // ===== epilogue: 4 warps, thread == output row == TMEM lane =====
-    const int lg = warp & 3;                                // TMEM lane group this warp may access
-    const int row = lg * 32 + lane;
     ptx::mbar_wait(bar_tmem, 0, g.err_flag, 13);
     ptx::tc_fence_after();
-    const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
     if (SPLIT == 1) {
       __half* crow = g.c + (int64_t)row * g.ldc + n0;
 #pragma unroll 1
@@ -168,12 +206,19 @@ __global__ void __launch_bounds__(G_THREADS, 1)
           }
         }
       }
-    } else {
+    }
+  }
+  if (SPLIT > 1) {
+    // every CTA of the cluster has retired its MMAs (its epilogue warps saw bar_tmem): the weight rings are dead and may
+    // receive the partial rows
+    if (!epi) __syncwarp();
+    cluster_sync_all();
+    if (epi) {
       // push this K-split's fp32 partial row to the CTA that owns the row (rows dealt in blocks of 128/SPLIT)
       constexpr int RPC = 128 / SPLIT;
       const uint32_t owner = (uint32_t)(row / RPC);
       uint32_t dst;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(s_base + SM::OFF_RED), "r"((uint32_t)mcr + MC * owner));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(s_w), "r"((uint32_t)mcr + MC * owner));
       dst += (uint32_t)((ks * RPC + row % RPC) * SM::R_STRIDE * 4);
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
@@ -193,18 +238,17 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 
   // (MC > 1: no CTA may leave while a peer can still multicast into its slots / arrive on its barriers;
   //  SPLIT > 1: the partial rows of every K-split must have landed in the owners' shared memory)
-  if (MC > 1 || SPLIT > 1)
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (MC > 1 || SPLIT > 1) cluster_sync_all();
 
   if (SPLIT > 1) {
     // owner CTA ks reduces rows [ks*RPC, (ks+1)*RPC): sum of the SPLIT slots in split order, fp16 out
     constexpr int RPC = 128 / SPLIT;
     constexpr int CPR = BN / 4;
-    const float* red = reinterpret_cast<const float*>(smem + SM::OFF_RED);
+    const float* red = reinterpret_cast<const float*>(smem + SM::OFF_W);
     for (int i = tid; i < RPC * CPR; i += G_THREADS) {
       const int lr = i / CPR, cc = i % CPR;
-      const int row = ks * RPC + lr;
-      if (row >= g.n) continue;
+      const int orow = ks * RPC + lr;
+      if (orow >= g.n) continue;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int s = 0; s < SPLIT; ++s) {
@@ -215,7 +259,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&lo);
       pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(g.c + (int64_t)row * g.ldc + n0 + cc * 4) = pk;
+      *reinterpret_cast<uint2*>(g.c + (int64_t)orow * g.ldc + n0 + cc * 4) = pk;
     }
   }
 }
@@ -299,7 +343,7 @@ extern "C" int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int ld
     const char* pe = getenv("SQ_PDL");
     p->pdl = (pe && atoi(pe)) ? 1 : 0;
   }
-  p->stages = p->split > 1 ? 4 : (p->bn >= 224 ? 4 : p->bn >= 160 ? 5 : p->bn >= 96 ? 6 : 8);   // == the dispatch table below
+  p->stages = gemm_sw(p->bn);                            // weight stages (activation stages: gemm_sa)
   int rc = encode_2d(&p->tm_a, a, (uint64_t)K, (uint64_t)n_max, (uint64_t)lda * 2, 64, (uint32_t)(128 / p->mc),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   if (!rc) rc = encode_2d(&p->tm_w, w, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 64, (uint32_t)p->bn, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
@@ -313,14 +357,14 @@ extern "C" int sq_gemm_plan_destroy(sq_gemm_plan* plan) {
   return SQ_OK;
 }
 
-template <int BN, int STAGES, int SPLIT, int MC>
+template <int BN, int SPLIT, int MC>
 static int launch_gemm(sq_gemm_plan* p, GemmArgs& g, cudaStream_t st) {
-  using SM = GemmSmem<BN, STAGES, SPLIT>;
+  using SM = GemmSmem<BN, SPLIT>;
   constexpr int smem = SM::TOTAL + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, SPLIT, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, SPLIT, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("sq_gemm: smem attr: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
     attr = true;
   }
@@ -341,7 +385,7 @@ static int launch_gemm(sq_gemm_plan* p, GemmArgs& g, cudaStream_t st) {
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, STAGES, SPLIT, MC>, p->tm_a, p->tm_w, g);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, SPLIT, MC>, p->tm_a, p->tm_w, g);
   if (e != cudaSuccess) { set_error("sq_gemm: launch failed: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
   SQ_CHECK_LAUNCH("sq_gemm");
   return SQ_OK;
@@ -357,14 +401,14 @@ extern "C" int sq_gemm_run(sq_gemm_plan* plan, int n, void* stream) {
   g.err_flag = plan->err_flag;
   cudaStream_t st = (cudaStream_t)stream;
   const int bn = plan->bn, sp = plan->split, mc = plan->mc;
-#define SQ_G(BN_, ST_, SP_, MC_) if (bn == BN_ && sp == SP_ && mc == MC_) return launch_gemm<BN_, ST_, SP_, MC_>(plan, g, st)
-  SQ_G(256, 4, 1, 1); SQ_G(256, 4, 1, 2);
-  SQ_G(224, 4, 1, 1); SQ_G(224, 4, 1, 2);
-  SQ_G(192, 5, 1, 1); SQ_G(192, 5, 1, 2);
-  SQ_G(160, 5, 1, 1); SQ_G(160, 5, 1, 2);
-  SQ_G(128, 6, 1, 1); SQ_G(128, 6, 1, 2); SQ_G(128, 4, 2, 1); SQ_G(128, 4, 4, 1); SQ_G(128, 4, 2, 2); SQ_G(128, 4, 4, 2);
-  SQ_G(96, 6, 1, 1); SQ_G(96, 6, 1, 2); SQ_G(96, 4, 2, 1); SQ_G(96, 4, 4, 1);
-  SQ_G(64, 8, 1, 1); SQ_G(64, 8, 1, 2); SQ_G(64, 4, 2, 1); SQ_G(64, 4, 4, 1); SQ_G(64, 4, 2, 2); SQ_G(64, 4, 4, 2);
+#define SQ_G(BN_, SP_, MC_) if (bn == BN_ && sp == SP_ && mc == MC_) return launch_gemm<BN_, SP_, MC_>(plan, g, st)
+  SQ_G(256, 1, 1); SQ_G(256, 1, 2);
+  SQ_G(224, 1, 1); SQ_G(224, 1, 2);
+  SQ_G(192, 1, 1); SQ_G(192, 1, 2);
+  SQ_G(160, 1, 1); SQ_G(160, 1, 2);
+  SQ_G(128, 1, 1); SQ_G(128, 1, 2); SQ_G(128, 2, 1); SQ_G(128, 4, 1); SQ_G(128, 2, 2); SQ_G(128, 4, 2);
+  SQ_G(96, 1, 1); SQ_G(96, 1, 2); SQ_G(96, 2, 1); SQ_G(96, 4, 1);
+  SQ_G(64, 1, 1); SQ_G(64, 1, 2); SQ_G(64, 2, 1); SQ_G(64, 4, 1); SQ_G(64, 2, 2); SQ_G(64, 4, 2);
 #undef SQ_G
   set_error("sq_gemm_run: no kernel for bn=%d split=%d mc=%d", bn, sp, mc);
   return SQ_ERR_UNSUPPORTED;

@@ -55,8 +55,8 @@ def get_sampling_logits(logits: torch.Tensor, top_p: float, T: float, replicate=
     if replicate:
         logits = logits.clone()
     if top_p < 1.0:
-        from .tree import _top_p_filter_
-        _top_p_filter_(logits, top_p, T)
+        shape = logits.shape
+        ops.top_p_filter_(logits.view(-1, shape[-1]), float(top_p), float(T))     # sq_top_p_filter kernel, in place
     return logits
 
 

@@ -295,19 +295,6 @@ class _Runtime:
         return sum(self.graph_launches.get(k, 0) * v for k, v in self.replays.items())
 
 
-def _top_p_filter_(logits: torch.Tensor, top_p: float, T: float):
-    """get_sampling_logits (utils.py:65-77) restated with torch ops -- NOT on the product path (that is the
-    `sq_top_p_filter` kernel, ops.top_p_filter_); kept as the on-device cross-check of tests/test_gpu_kernels.py."""
-    sorted_logits, sorted_indices = torch.sort(logits, descending=True)
-    cumulative_probs = torch.cumsum(torch.softmax(sorted_logits / T, dim=-1), dim=-1)
-    filt = cumulative_probs > top_p
-    filt[..., 1:] = filt[..., :-1].clone()
-    filt[..., 0] = 0
-    indices_to_remove = filt.scatter(-1, sorted_indices, filt)
-    logits.masked_fill_(indices_to_remove, float("-inf"))     # (boolean-index assignment would sync: not capturable)
-    return logits
-
-
 _RUNTIMES: Dict[tuple, _Runtime] = {}
 
 
