@@ -195,13 +195,26 @@ int sq_l2_prefetch(const void* base, int64_t pitch_bytes, int rows, int64_t off_
 /* C[n, N] = A[n, K] * W[N, K]^T, fp16 in / fp32 accumulate / fp16 out, n <= 128.  A: (n_max, lda), W: (N, K) row-major
  * (the nn.Linear weight as stored), C: (n_max, ldc).  K % 64 == 0, N % 128 == 0.  Plans hold the TMA descriptors; create
  * once per (activation buffer, weight, output buffer), run inside graphs.  err_flag: optional device word set by the
- * pipeline watchdog.  Larger n (prefill) stays on cuBLASLt. */
+ * pipeline watchdog.  n > 128 (prefill) runs one launch per 128-row tile. */
 typedef struct sq_gemm_plan sq_gemm_plan;
 int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N, int K,
                         sq_half* c, int ldc, int* err_flag);
+/* Tile shape (BN, K splits, multicast width) a plan for (N, K) will use -- needed to pre-tile weights. */
+int sq_gemm_pick_tiles(int N, int K, int* bn, int* split, int* mc);
+/* As sq_gemm_plan_create, for weights stored pre-tiled as (ceil(N/BN), K/64, BN, 64) fp16 contiguous (rows beyond N
+ * zero): every weight TMA load is one contiguous BN*128-byte block of HBM. */
+int sq_gemm_plan_create_tiled(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w_tiled, int N, int K,
+                              sq_half* c, int ldc, int* err_flag);
+/* Fused epilogue.  kind 0: plain (default).  kind 1 (SwiGLU, Engine/Llama_modules.py:272): W's rows interleave 16 gate
+ * rows / 16 up rows (row 32b+t = gate[16b+t], row 32b+16+t = up[16b+t]); C (n, n_out = N/2) = silu(gate) * up with the
+ * reference's fp16 rounding points.  Not for split-K plans. */
+int sq_gemm_plan_set_epilogue(sq_gemm_plan* plan, int kind, int n_out);
 int sq_gemm_plan_destroy(sq_gemm_plan* plan);
 int sq_gemm_plan_info(sq_gemm_plan* plan, int* bn, int* split, int* stages);
 int sq_gemm_run(sq_gemm_plan* plan, int n, void* stream);
+/* Rows [a_row0, a_row0 + n) of the plan's activation buffer -> rows [0, n) of `c` (pitch ldc halfs); c == NULL: the plan's
+ * own output buffer, rows [a_row0, a_row0 + n). */
+int sq_gemm_run_at(sq_gemm_plan* plan, int n, int a_row0, sq_half* c, int ldc, void* stream);
 
 /* ---- target tensor parallelism: fused one-shot all-reduce over NVLink peer memory (no reference counterpart) ---- */
 

@@ -46,9 +46,13 @@ _SIGNATURES = {
     "sq_accept_greedy": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]),
     "sq_l2_prefetch": (i32, [vp, i64, i32, i64, i64, vp]),
     "sq_gemm_plan_create": (i32, [C.POINTER(vp), vp, i32, i32, vp, i32, i32, vp, i32, vp]),
+    "sq_gemm_pick_tiles": (i32, [i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "sq_gemm_plan_create_tiled": (i32, [C.POINTER(vp), vp, i32, i32, vp, i32, i32, vp, i32, vp]),
+    "sq_gemm_plan_set_epilogue": (i32, [vp, i32, i32]),
     "sq_gemm_plan_destroy": (i32, [vp]),
     "sq_gemm_plan_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "sq_gemm_run": (i32, [vp, i32, vp]),
+    "sq_gemm_run_at": (i32, [vp, i32, i32, vp, i32, vp]),
     "sq_tp_alloc": (i32, [C.POINTER(vp), i64]),
     "sq_tp_free": (i32, [vp]),
     "sq_tp_ipc_export": (i32, [vp, vp]),

@@ -2,10 +2,9 @@
 // in tensor memory, fp16 out) -- nn.Linear of the target / draft forward (Engine/Llama_modules.py:108-110,138,270-272,
 // Llama_model.py:213) for at most 128 rows.  With 128 rows every weight byte is used once: the kernel is a pure HBM
 // stream (roofline = weight bytes / HBM bandwidth), so the design goal is bytes in flight, not FLOPs:
-//   * one CTA per BN-wide slice of N (one wave on 148 SMs), warp-specialised: a weight-TMA lane, an activation-TMA
-//     lane, an MMA issuer lane, 4 epilogue warps; TWO mbarrier rings of SWIZZLE_128B tiles -- 10-20 weight stages
-//     (BN x 64, 156-168 KB of HBM bytes in flight per SM) and 3-4 activation stages (128 x 64, from L2);
-//     tcgen05.mma kind::f16 M=128 N=BN K=16, accumulator in TMEM;
+//   * one CTA per 128- or 256-wide slice of N (one wave on 148 SMs), warp-specialised: 1 TMA producer lane, 1 MMA
+//     issuer lane, 4 epilogue warps; a 4-6 stage mbarrier ring of (A 128x64, W BNx64) SWIZZLE_128B tiles keeps
+//     128-192 KB per SM in flight; tcgen05.mma kind::f16 M=128 N=BN K=16, accumulator in TMEM;
 //   * narrow outputs (o_proj / down_proj: N = hidden = 32 slices only) are split along K over a thread-block cluster
 //     (1, SPLIT, 1): each CTA streams 1/SPLIT of K, pushes its fp32 partial rows into the shared memory of the row's
 //     owner CTA (st.shared::cluster), one cluster barrier, owners add in a fixed order and store fp16.
@@ -18,7 +17,7 @@
 struct sq_gemm_plan {
   CUtensorMap tm_a, tm_w;
   __half* c;
-  int ldc, n_max, N, K, bn, split, stages, mc, pdl;
+  int ldc, n_max, N, K, bn, split, stages, mc, pdl, tiled, epi, n_out;
   int* err_flag;
 };
 
@@ -27,41 +26,27 @@ namespace sq {
 struct GemmArgs {
   __half* c;
   int ldc, n, N, K, kb_per_split;   // kb = 64-wide K blocks handled by one CTA
+  int tiled, kb_total;              // weights pre-tiled: tile (n-tile, kb) is one contiguous BN x 64 block
+  int m0;                           // first activation / output row of this launch (row tiles of 128 for n > 128)
+  int epi, n_out;                   // epi 1: weight rows interleave 16 gate | 16 up rows -> out = silu(gate) * up, n_out columns
   int* err_flag;
 };
 
 constexpr int G_BK = 64;
-constexpr int G_THREADS = 224;       // warp 0: weight TMA, warp 1: MMA + TMEM alloc, warp 2: activation TMA, warps 3..6: epilogue
+constexpr int G_THREADS = 192;       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
 
 __host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
-// Two INDEPENDENT rings.  What bounds a 128-row weight stream is the number of HBM bytes each SM keeps in flight
-// (Little: ~6.5 TB/s x ~2 us loaded latency = 13 MB over 148 SMs = ~90 KB per SM of WEIGHT bytes); the activation
-// slab comes from L2 (short latency, re-read by every CTA) and needs only a few stages.  With one coupled ring every
-// stage carries a 16 KB activation tile, i.e. half of the shared memory holds L2-resident data (ncu, round 2: 72 KB of
-// weight bytes in flight per CTA at BN=96 vs 124 KB in cuBLASLt's 2-CTA kernel).  Here: SA (3-4) activation stages and
-// as many weight stages as the rest of the 227 KB holds (156-168 KB).
-__host__ __device__ constexpr int gemm_sa(int bn) { return bn >= 192 ? 3 : 4; }
-__host__ __device__ constexpr int gemm_wpad(int bn) { return ((bn * 128 + 1023) / 1024) * 1024; }
-__host__ __device__ constexpr int gemm_sw(int bn) { return (220 * 1024 - gemm_sa(bn) * 16384) / gemm_wpad(bn); }
-
-template <int BN, int SPLIT>
+template <int BN, int STAGES, int SPLIT>
 struct GemmSmem {
-  static constexpr int SA = gemm_sa(BN), SW = gemm_sw(BN);
   static constexpr int A_BYTES = 128 * 128;            // 128 rows x 64 halfs
   static constexpr int W_BYTES = BN * 128;
-  static constexpr int W_PAD = gemm_wpad(BN);          // stages stay 1024 B aligned (SW128)
-  static constexpr int OFF_W = 0;
-  static constexpr int OFF_A = SW * W_PAD;
-  static constexpr int OFF_BAR = OFF_A + SA * A_BYTES; // full_w[SW], empty_w[SW], full_a[SA], empty_a[SA], tmem_full, tmem ptr
-  static constexpr int BAR_BYTES = 512;
-  static_assert((2 * SW + 2 * SA + 2) * 8 <= BAR_BYTES, "barrier block");
-  // split-K: SPLIT slots x (128/SPLIT rows) x (BN+4) floats, ALIASED onto the weight ring (dead once every CTA of the
-  // cluster has retired its MMAs: a cluster barrier separates the main loops from the pushes)
+  static constexpr int STAGE_BYTES = A_BYTES + ((W_BYTES + 1023) / 1024) * 1024;   // stages stay 1024 B aligned (SW128)
+  static constexpr int OFF_BAR = STAGES * STAGE_BYTES; // full[STAGES], empty[STAGES], tmem_full, tmem ptr
+  static constexpr int OFF_RED = OFF_BAR + 256;        // split-K: SPLIT slots x (128/SPLIT rows) x (BN+4) floats
   static constexpr int R_STRIDE = BN + 4;
   static constexpr int RED_BYTES = SPLIT > 1 ? 128 * R_STRIDE * 4 : 0;
-  static_assert(RED_BYTES <= SW * W_PAD, "reduction buffers must fit the weight ring");
-  static constexpr int TOTAL = OFF_BAR + BAR_BYTES;
+  static constexpr int TOTAL = OFF_RED + RED_BYTES;
 };
 
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
@@ -74,18 +59,14 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 // MC = CTAs (along N) that share one activation K-slab: each loads 128/MC of its rows and multicasts them to all.
-template <int BN, int SPLIT, int MC>
+template <int BN, int STAGES, int SPLIT, int MC>
 __global__ void __launch_bounds__(G_THREADS, 1)
     gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, GemmArgs g) {
   // cluster (MC, SPLIT): rank = mcr + MC * ks.  CTAs with the same ks share the activation slab (multicast group); CTAs
   // with the same mcr hold the K-splits of one output tile (DSMEM reduction group).
-  using SM = GemmSmem<BN, SPLIT>;
-  constexpr int SW = SM::SW, SA = SM::SA;
+  using SM = GemmSmem<BN, STAGES, SPLIT>;
   constexpr int TCOLS = tmem_cols_for(BN);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -96,22 +77,14 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   const int kb0 = ks * g.kb_per_split;
   const int nkb = g.kb_per_split;
   const uint32_t s_base = ptx::smem_u32(smem);
-  const uint32_t s_w = s_base + SM::OFF_W, s_a = s_base + SM::OFF_A;
-  const uint32_t full_w = s_base + SM::OFF_BAR, empty_w = full_w + 8 * SW, full_a = empty_w + 8 * SW,
-                 empty_a = full_a + 8 * SA, bar_tmem = empty_a + 8 * SA;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + (2 * SW + 2 * SA + 1) * 8);
-  const uint16_t mc_mask = (uint16_t)(((1u << MC) - 1u) << (MC * ks));
+  const uint32_t bar_full = s_base + SM::OFF_BAR, bar_empty = bar_full + 8 * STAGES, bar_tmem = bar_empty + 8 * STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + 16 * STAGES + 8);
 
   if (tid == 0) {
-#pragma unroll 1
-    for (int s = 0; s < SW; ++s) {
-      ptx::mbar_init(full_w + 8 * s, 1);
-      ptx::mbar_init(empty_w + 8 * s, 1);
-    }
 #pragma unroll
-    for (int s = 0; s < SA; ++s) {
-      ptx::mbar_init(full_a + 8 * s, 1);
-      ptx::mbar_init(empty_a + 8 * s, MC);                 // every CTA that received this slot's rows must release it
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, MC);               // every CTA that received this slot's A rows must release it
     }
     ptx::mbar_init(bar_tmem, 1);
     ptx::fence_barrier_init();
@@ -122,76 +95,92 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (MC > 1) cluster_sync_all();   // the peers' barriers must be initialised before any multicast / remote arrive targets them
+  if (MC > 1)   // the peers' barriers must be initialised before any multicast / remote arrive can target them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===== weight producer: never waits for the previous kernel (weights are constants), so under programmatic
-    // dependent launch the whole ring fills while that kernel is still draining =====
+    // ===== TMA producer =====
     if (lane == 0) {
       asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-      int stage = 0;
-      uint32_t phase = 0;
-#pragma unroll 1
-      for (int kb = 0; kb < nkb; ++kb) {
-        if (kb >= SW) ptx::mbar_wait_one(empty_w + 8 * stage, phase ^ 1, g.err_flag, 11);
-        ptx::mbar_expect_tx(full_w + 8 * stage, SM::W_BYTES);
-        ptx::tma_load_2d(s_w + stage * SM::W_PAD, &tm_w, full_w + 8 * stage, (kb0 + kb) * G_BK, n0);
-        if (++stage == SW) { stage = 0; phase ^= 1; }
+      // Weights do not depend on the previous kernel: under programmatic dependent launch the first ring of weight
+      // tiles streams in while that kernel is still running; only the activation loads wait for it.
+      const int pre = nkb < STAGES ? nkb : STAGES;
+      for (int kb = 0; kb < pre; ++kb) {
+        const uint32_t sa = s_base + kb * SM::STAGE_BYTES, sw = sa + SM::A_BYTES;
+        ptx::mbar_expect_tx(bar_full + 8 * kb, SM::A_BYTES + SM::W_BYTES);
+        if (g.tiled) ptx::tma_load_2d(sw, &tm_w, bar_full + 8 * kb, 0, ((int)blockIdx.x * g.kb_total + kb0 + kb) * BN);
+        else ptx::tma_load_2d(sw, &tm_w, bar_full + 8 * kb, (kb0 + kb) * G_BK, n0);
       }
-    }
-  } else if (warp == 2) {
-    // ===== activation producer =====
-    if (lane == 0) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
       int stage = 0;
       uint32_t phase = 0;
-#pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb) {
-        if (kb >= SA) ptx::mbar_wait_one(empty_a + 8 * stage, phase ^ 1, g.err_flag, 14);   // slot free in EVERY CTA of the group
-        ptx::mbar_expect_tx(full_a + 8 * stage, SM::A_BYTES);
-        const uint32_t sa = s_a + stage * SM::A_BYTES;
-        if (MC == 1) ptx::tma_load_2d(sa, &tm_a, full_a + 8 * stage, (kb0 + kb) * G_BK, 0);
-        else tma_load_2d_mc(sa + mcr * (SM::A_BYTES / MC), &tm_a, full_a + 8 * stage, (kb0 + kb) * G_BK, mcr * (128 / MC), mc_mask);
-        if (++stage == SA) { stage = 0; phase ^= 1; }
+        const uint32_t sa = s_base + stage * SM::STAGE_BYTES, sw = sa + SM::A_BYTES;
+        if (kb >= pre) {
+          ptx::mbar_wait_one(bar_empty + 8 * stage, phase ^ 1, g.err_flag, 11);   // slot free in EVERY CTA of the cluster
+          ptx::mbar_expect_tx(bar_full + 8 * stage, SM::A_BYTES + SM::W_BYTES);
+          if (g.tiled) ptx::tma_load_2d(sw, &tm_w, bar_full + 8 * stage, 0, ((int)blockIdx.x * g.kb_total + kb0 + kb) * BN);
+          else ptx::tma_load_2d(sw, &tm_w, bar_full + 8 * stage, (kb0 + kb) * G_BK, n0);
+        }
+        if (MC == 1) ptx::tma_load_2d(sa, &tm_a, bar_full + 8 * stage, (kb0 + kb) * G_BK, g.m0);
+        else tma_load_2d_mc(sa + mcr * (SM::A_BYTES / MC), &tm_a, bar_full + 8 * stage, (kb0 + kb) * G_BK, g.m0 + mcr * (128 / MC),
+                            (uint16_t)(((1u << MC) - 1u) << (MC * ks)));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(BN, false);
-      int sw = 0, sa = 0;
-      uint32_t pw = 0, pa = 0;
-#pragma unroll 1
+      int stage = 0;
+      uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        ptx::mbar_wait_one(full_a + 8 * sa, pa, g.err_flag, 12);
-        ptx::mbar_wait_one(full_w + 8 * sw, pw, g.err_flag, 15);
+        ptx::mbar_wait_one(bar_full + 8 * stage, phase, g.err_flag, 12);           // TMA bytes have landed
         ptx::tc_fence_after();
-        const uint32_t a_addr = s_a + sa * SM::A_BYTES, w_addr = s_w + sw * SM::W_PAD;
+        const uint32_t sa = s_base + stage * SM::STAGE_BYTES, sw = sa + SM::A_BYTES;
 #pragma unroll
         for (int k = 0; k < G_BK / 16; ++k)
-          ptx::mma_ss(tmem, umma_desc(a_addr + k * 32, 16, 1024), umma_desc(w_addr + k * 32, 16, 1024), idesc, (kb | k) != 0);
-        // the slots are free when these MMAs retire -- the activation slot in every CTA that multicasts into it
-        ptx::tc_commit(empty_w + 8 * sw);
-        if (MC == 1) ptx::tc_commit(empty_a + 8 * sa);
-        else tc_commit_mc(empty_a + 8 * sa, mc_mask);
-        if (++sw == SW) { sw = 0; pw ^= 1; }
-        if (++sa == SA) { sa = 0; pa ^= 1; }
+          ptx::mma_ss(tmem, umma_desc(sa + k * 32, 16, 1024), umma_desc(sw + k * 32, 16, 1024), idesc, (kb | k) != 0);
+        // frees the slot when the MMAs retire -- in every CTA whose multicast writes into this CTA's slot
+        if (MC == 1) ptx::tc_commit(bar_empty + 8 * stage);
+        else tc_commit_mc(bar_empty + 8 * stage, (uint16_t)(((1u << MC) - 1u) << (MC * ks)));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       ptx::tc_commit(bar_tmem);                                                    // accumulator complete
     }
-  }
-  const bool epi = warp >= 3;
-  const int lg = warp & 3;                                  // TMEM lane group this warp may access
-  const int row = lg * 32 + lane;
-  const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
-  if (epi) {
+  } else {
     // ===== epilogue: 4 warps, thread == output row == TMEM lane =====
+    const int lg = warp & 3;                                // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;
     ptx::mbar_wait(bar_tmem, 0, g.err_flag, 13);
     ptx::tc_fence_after();
-    if (SPLIT == 1) {
-      __half* crow = g.c + (int64_t)row * g.ldc + n0;
+    const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
+    if (SPLIT == 1 && g.epi == 1) {
+      // fused SwiGLU epilogue (Engine/Llama_modules.py:272: down(act(gate(x)) * up(x))): the weight rows interleave 16 gate
+      // rows with their 16 up rows, so a 32-column accumulator chunk holds both halves of 16 outputs.  Rounding points of the
+      // unfused path: gate, up -> fp16; silu in fp32 -> fp16; product -> fp16.
+      __half* orow = g.c + (int64_t)(g.m0 + row) * g.ldc;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem + lane_base + j * 32, r);
+        const int oc = (n0 + j * 32) / 2;
+        if (row < g.n && oc < g.n_out) {
+          Pack8 o[2];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float x = h2f(f2h(__uint_as_float(r[e])));
+            const __half act = f2h(x / (1.0f + expf(-x)));
+            o[e / 8].h[e % 8] = f2h(h2f(act) * h2f(f2h(__uint_as_float(r[16 + e]))));
+          }
+          *reinterpret_cast<uint4*>(orow + oc) = o[0].u;
+          *reinterpret_cast<uint4*>(orow + oc + 8) = o[1].u;
+        }
+      }
+    } else if (SPLIT == 1) {
+      __half* crow = g.c + (int64_t)(g.m0 + row) * g.ldc + n0;
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
         uint32_t r[32];
@@ -206,19 +195,12 @@ __global__ void __launch_bounds__(G_THREADS, 1)
           }
         }
       }
-    }
-  }
-  if (SPLIT > 1) {
-    // every CTA of the cluster has retired its MMAs (its epilogue warps saw bar_tmem): the weight rings are dead and may
-    // receive the partial rows
-    if (!epi) __syncwarp();
-    cluster_sync_all();
-    if (epi) {
+    } else {
       // push this K-split's fp32 partial row to the CTA that owns the row (rows dealt in blocks of 128/SPLIT)
       constexpr int RPC = 128 / SPLIT;
       const uint32_t owner = (uint32_t)(row / RPC);
       uint32_t dst;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(s_w), "r"((uint32_t)mcr + MC * owner));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(s_base + SM::OFF_RED), "r"((uint32_t)mcr + MC * owner));
       dst += (uint32_t)((ks * RPC + row % RPC) * SM::R_STRIDE * 4);
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
@@ -238,17 +220,18 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 
   // (MC > 1: no CTA may leave while a peer can still multicast into its slots / arrive on its barriers;
   //  SPLIT > 1: the partial rows of every K-split must have landed in the owners' shared memory)
-  if (MC > 1 || SPLIT > 1) cluster_sync_all();
+  if (MC > 1 || SPLIT > 1)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 
   if (SPLIT > 1) {
     // owner CTA ks reduces rows [ks*RPC, (ks+1)*RPC): sum of the SPLIT slots in split order, fp16 out
     constexpr int RPC = 128 / SPLIT;
     constexpr int CPR = BN / 4;
-    const float* red = reinterpret_cast<const float*>(smem + SM::OFF_W);
+    const float* red = reinterpret_cast<const float*>(smem + SM::OFF_RED);
     for (int i = tid; i < RPC * CPR; i += G_THREADS) {
       const int lr = i / CPR, cc = i % CPR;
-      const int orow = ks * RPC + lr;
-      if (orow >= g.n) continue;
+      const int row = ks * RPC + lr;
+      if (row >= g.n) continue;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int s = 0; s < SPLIT; ++s) {
@@ -259,7 +242,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&lo);
       pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(g.c + (int64_t)orow * g.ldc + n0 + cc * 4) = pk;
+      *reinterpret_cast<uint2*>(g.c + (int64_t)(g.m0 + row) * g.ldc + n0 + cc * 4) = pk;
     }
   }
 }
@@ -321,13 +304,8 @@ static void choose_tiles(sq_gemm_plan* p) {
   p->bn = best_bn; p->split = best_split; p->mc = best_mc;
 }
 
-extern "C" int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N,
-                                   int K, sq_half* c, int ldc, int* err_flag) {
-  SQ_CHECK_ARG(plan && a && w && c, "sq_gemm_plan_create: null pointer");
-  SQ_CHECK_ARG(K % 64 == 0 && N % 32 == 0 && lda % 8 == 0 && ldc % 8 == 0, "sq_gemm_plan_create: K %% 64, N %% 32");
-  sq_gemm_plan* p = new sq_gemm_plan();
-  p->c = (__half*)c; p->ldc = ldc; p->n_max = n_max; p->N = N; p->K = K; p->err_flag = err_flag;
-  const int kb = K / 64;
+static void pick_tiles(sq_gemm_plan* p) {
+  const int kb = p->K / 64;
   choose_tiles(p);
   const char* force = getenv("SQ_GEMM_FORCE");          // tuning / debugging: "bn,split,mc"
   if (force) {
@@ -335,18 +313,58 @@ extern "C" int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int ld
     const int nf = sscanf(force, "%d,%d,%d", &fb, &fs, &fm);
     const bool bn_ok = fb == 64 || fb == 96 || fb == 128 || fb == 160 || fb == 192 || fb == 224 || fb == 256;
     if (nf >= 2 && bn_ok && (fs == 1 || fs == 2 || fs == 4) && kb % fs == 0 && (fm == 1 || fm == 2) &&
-        !(fs > 1 && (fb > 128 || N % fb)) && !(fm == 2 && ((N + fb - 1) / fb) % 2)) {
+        !(fs > 1 && (fb > 128 || p->N % fb)) && !(fm == 2 && ((p->N + fb - 1) / fb) % 2)) {
       p->bn = fb; p->split = fs; p->mc = fm;
     }
   }
+}
+
+/* The tile shape a plan for (N, K) will use: callers that pre-tile the weights need BN before they build the copy. */
+extern "C" int sq_gemm_pick_tiles(int N, int K, int* bn, int* split, int* mc) {
+  SQ_CHECK_ARG(K % 64 == 0 && N % 32 == 0, "sq_gemm_pick_tiles: K %% 64, N %% 32");
+  sq_gemm_plan p{};
+  p.N = N; p.K = K;
+  pick_tiles(&p);
+  *bn = p.bn; *split = p.split; *mc = p.mc;
+  return SQ_OK;
+}
+
+static int plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N, int K, sq_half* c,
+                       int ldc, int* err_flag, int tiled);
+
+extern "C" int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N,
+                                   int K, sq_half* c, int ldc, int* err_flag) {
+  return plan_create(plan, a, lda, n_max, w, N, K, c, ldc, err_flag, 0);
+}
+
+/* Same, for weights stored PRE-TILED: (ceil(N/BN), K/64, BN, 64) fp16 contiguous (rows beyond N zero), BN from
+ * sq_gemm_pick_tiles -- every TMA weight load is then ONE contiguous BN*128-byte block of HBM instead of BN separate
+ * 128-byte segments K*2 bytes apart. */
+extern "C" int sq_gemm_plan_create_tiled(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w_tiled,
+                                         int N, int K, sq_half* c, int ldc, int* err_flag) {
+  return plan_create(plan, a, lda, n_max, w_tiled, N, K, c, ldc, err_flag, 1);
+}
+
+static int plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N, int K, sq_half* c,
+                       int ldc, int* err_flag, int tiled) {
+  SQ_CHECK_ARG(plan && a && w && c, "sq_gemm_plan_create: null pointer");
+  SQ_CHECK_ARG(K % 64 == 0 && N % 32 == 0 && lda % 8 == 0 && ldc % 8 == 0, "sq_gemm_plan_create: K %% 64, N %% 32");
+  sq_gemm_plan* p = new sq_gemm_plan();
+  p->c = (__half*)c; p->ldc = ldc; p->n_max = n_max; p->N = N; p->K = K; p->err_flag = err_flag;
+  p->tiled = tiled; p->epi = 0; p->n_out = 0;
+  pick_tiles(p);
   {
     const char* pe = getenv("SQ_PDL");
     p->pdl = (pe && atoi(pe)) ? 1 : 0;
   }
-  p->stages = gemm_sw(p->bn);                            // weight stages (activation stages: gemm_sa)
+  p->stages = p->split > 1 ? 4 : (p->bn >= 224 ? 4 : p->bn >= 160 ? 5 : p->bn >= 96 ? 6 : 8);   // == the dispatch table below
   int rc = encode_2d(&p->tm_a, a, (uint64_t)K, (uint64_t)n_max, (uint64_t)lda * 2, 64, (uint32_t)(128 / p->mc),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
-  if (!rc) rc = encode_2d(&p->tm_w, w, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 64, (uint32_t)p->bn, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (!rc) {
+    if (tiled) rc = encode_2d(&p->tm_w, w, 64, (uint64_t)((N + p->bn - 1) / p->bn) * (uint64_t)(K / 64) * (uint64_t)p->bn, 128, 64,
+                              (uint32_t)p->bn, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    else rc = encode_2d(&p->tm_w, w, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 64, (uint32_t)p->bn, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  }
   if (rc) { delete p; return rc; }
   *plan = p;
   return SQ_OK;
@@ -357,14 +375,14 @@ extern "C" int sq_gemm_plan_destroy(sq_gemm_plan* plan) {
   return SQ_OK;
 }
 
-template <int BN, int SPLIT, int MC>
+template <int BN, int STAGES, int SPLIT, int MC>
 static int launch_gemm(sq_gemm_plan* p, GemmArgs& g, cudaStream_t st) {
-  using SM = GemmSmem<BN, SPLIT>;
+  using SM = GemmSmem<BN, STAGES, SPLIT>;
   constexpr int smem = SM::TOTAL + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, SPLIT, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, SPLIT, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("sq_gemm: smem attr: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
     attr = true;
   }
@@ -385,33 +403,60 @@ static int launch_gemm(sq_gemm_plan* p, GemmArgs& g, cudaStream_t st) {
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, SPLIT, MC>, p->tm_a, p->tm_w, g);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, STAGES, SPLIT, MC>, p->tm_a, p->tm_w, g);
   if (e != cudaSuccess) { set_error("sq_gemm: launch failed: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
   SQ_CHECK_LAUNCH("sq_gemm");
   return SQ_OK;
 }
 
-extern "C" int sq_gemm_run(sq_gemm_plan* plan, int n, void* stream) {
-  SQ_CHECK_ARG(plan != nullptr, "sq_gemm_run: null plan");
-  SQ_CHECK_ARG(n >= 0 && n <= 128 && n <= plan->n_max, "sq_gemm_run: n=%d must be <= 128 (and <= n_max)", n);
-  if (n == 0) return SQ_OK;
-  GemmArgs g;
-  g.c = plan->c; g.ldc = plan->ldc; g.n = n; g.N = plan->N; g.K = plan->K;
-  g.kb_per_split = plan->K / 64 / plan->split;
-  g.err_flag = plan->err_flag;
-  cudaStream_t st = (cudaStream_t)stream;
+static int run_tile(sq_gemm_plan* plan, GemmArgs& g, cudaStream_t st) {
   const int bn = plan->bn, sp = plan->split, mc = plan->mc;
-#define SQ_G(BN_, SP_, MC_) if (bn == BN_ && sp == SP_ && mc == MC_) return launch_gemm<BN_, SP_, MC_>(plan, g, st)
-  SQ_G(256, 1, 1); SQ_G(256, 1, 2);
-  SQ_G(224, 1, 1); SQ_G(224, 1, 2);
-  SQ_G(192, 1, 1); SQ_G(192, 1, 2);
-  SQ_G(160, 1, 1); SQ_G(160, 1, 2);
-  SQ_G(128, 1, 1); SQ_G(128, 1, 2); SQ_G(128, 2, 1); SQ_G(128, 4, 1); SQ_G(128, 2, 2); SQ_G(128, 4, 2);
-  SQ_G(96, 1, 1); SQ_G(96, 1, 2); SQ_G(96, 2, 1); SQ_G(96, 4, 1);
-  SQ_G(64, 1, 1); SQ_G(64, 1, 2); SQ_G(64, 2, 1); SQ_G(64, 4, 1); SQ_G(64, 2, 2); SQ_G(64, 4, 2);
+#define SQ_G(BN_, ST_, SP_, MC_) if (bn == BN_ && sp == SP_ && mc == MC_) return launch_gemm<BN_, ST_, SP_, MC_>(plan, g, st)
+  SQ_G(256, 4, 1, 1); SQ_G(256, 4, 1, 2);
+  SQ_G(224, 4, 1, 1); SQ_G(224, 4, 1, 2);
+  SQ_G(192, 5, 1, 1); SQ_G(192, 5, 1, 2);
+  SQ_G(160, 5, 1, 1); SQ_G(160, 5, 1, 2);
+  SQ_G(128, 6, 1, 1); SQ_G(128, 6, 1, 2); SQ_G(128, 4, 2, 1); SQ_G(128, 4, 4, 1); SQ_G(128, 4, 2, 2); SQ_G(128, 4, 4, 2);
+  SQ_G(96, 6, 1, 1); SQ_G(96, 6, 1, 2); SQ_G(96, 4, 2, 1); SQ_G(96, 4, 4, 1);
+  SQ_G(64, 8, 1, 1); SQ_G(64, 8, 1, 2); SQ_G(64, 4, 2, 1); SQ_G(64, 4, 4, 1); SQ_G(64, 4, 2, 2); SQ_G(64, 4, 4, 2);
 #undef SQ_G
   set_error("sq_gemm_run: no kernel for bn=%d split=%d mc=%d", bn, sp, mc);
   return SQ_ERR_UNSUPPORTED;
+}
+
+extern "C" int sq_gemm_run(sq_gemm_plan* plan, int n, void* stream) { return sq_gemm_run_at(plan, n, 0, nullptr, 0, stream); }
+
+/* rows [a_row0, a_row0 + n) of the plan's activation buffer -> rows [0, n) of `c` (pitch ldc halfs; NULL = the plan's own
+ * output buffer, rows [a_row0, ...)). */
+extern "C" int sq_gemm_run_at(sq_gemm_plan* plan, int n, int a_row0, sq_half* c, int ldc, void* stream) {
+  SQ_CHECK_ARG(plan != nullptr, "sq_gemm_run: null plan");
+  SQ_CHECK_ARG(n >= 0 && a_row0 >= 0 && a_row0 + n <= plan->n_max, "sq_gemm_run: rows [%d, %d) exceed the plan's n_max=%d", a_row0, a_row0 + n, plan->n_max);
+  SQ_CHECK_ARG(c == nullptr || (ldc % 8 == 0 && ((uintptr_t)c % 16) == 0), "sq_gemm_run: output override must be 16 B aligned, pitch %% 8");
+  // more than 128 rows (prefill): one launch per 128-row tile, each streaming the weights again (once per prompt)
+  for (int m0 = 0; m0 < n; m0 += 128) {
+    GemmArgs g;
+    g.n = n - m0 < 128 ? n - m0 : 128; g.N = plan->N; g.K = plan->K;
+    g.kb_per_split = plan->K / 64 / plan->split;
+    g.tiled = plan->tiled; g.kb_total = plan->K / 64;
+    g.m0 = a_row0 + m0; g.epi = plan->epi; g.n_out = plan->n_out;
+    // the kernel addresses output row (g.m0 + row): bias the base so that activation row a_row0 lands on output row 0
+    if (c) { g.ldc = ldc; g.c = (__half*)c - (int64_t)a_row0 * ldc; }
+    else { g.ldc = plan->ldc; g.c = plan->c; }
+    g.err_flag = plan->err_flag;
+    const int rc = run_tile(plan, g, (cudaStream_t)stream);
+    if (rc != SQ_OK) return rc;
+  }
+  return SQ_OK;
+}
+
+/* Fused epilogue.  kind 0: C = A W^T (default).  kind 1 (SwiGLU): the weight rows interleave 16 gate rows / 16 up rows
+ * (row 32b + t = gate[16b + t], row 32b + 16 + t = up[16b + t]); C (n, n_out = N/2) = silu(gate) * up.  Split-K plans
+ * cannot fuse it. */
+extern "C" int sq_gemm_plan_set_epilogue(sq_gemm_plan* plan, int kind, int n_out) {
+  SQ_CHECK_ARG(plan != nullptr && (kind == 0 || kind == 1), "sq_gemm_plan_set_epilogue: bad arguments");
+  SQ_CHECK_ARG(kind == 0 || (plan->split == 1 && n_out % 16 == 0 && 2 * n_out <= plan->N + 31), "sq_gemm_plan_set_epilogue: SwiGLU needs split 1, n_out %% 16 == 0");
+  plan->epi = kind; plan->n_out = n_out;
+  return SQ_OK;
 }
 
 extern "C" int sq_gemm_plan_info(sq_gemm_plan* plan, int* bn, int* split, int* stages) {

@@ -244,20 +244,33 @@ class LlamaRunner:
         self.k_cache = torch.zeros(self.L, 1, self.Hkv, max_length, D, dtype=F16, device=dev)
         self.v_cache = torch.zeros_like(self.k_cache)
         self.plan = ops.AttnPlan(self.qkv, n, self.H, self.Hkv, D, self.k_cache, self.v_cache, self.attn_out)
-        # TP: the row-parallel GEMMs write into NVLink peer-visible buffers and ONE kernel does all-reduce + residual +
-        # RMSNorm (csrc/sq_tp.cu).  SQ_TP_MODE=nccl keeps torch.distributed.all_reduce + sq_add_rmsnorm (baseline).
-        # Optional hand-written weight-streaming GEMM (csrc/sq_gemm.cu) for forwards of <= 128 rows.  OFF by default:
-        # in round 1 it is bit-compatible with cuBLASLt but not yet faster, so the dense GEMMs
-        # stay on cuBLASLt as SURVEY.md 2.2 K1 prescribes.  SQ_GEMM=1 turns it on (tests / tuning).
+        # Dense GEMMs.  Default ("auto"): the weight-streaming shapes that the hand-written tcgen05 kernel (csrc/sq_gemm.cu)
+        # wins -- gate_up with the SwiGLU epilogue fused (weights interleaved + pre-tiled, `act` written directly: no
+        # gate_up round trip, no silu_mul launch) and the target's lm_head (pre-tiled) -- for models whose layers are
+        # HBM-stream-sized (hidden >= 2048); q/k/v, o_proj and down_proj stay on cuBLASLt (torch.mm), whose 2-CTA-MMA
+        # kernels are faster at those shapes (profiles/r02_gemm_ncu.md).  SQ_GEMM=1 routes those through sq_gemm too
+        # (tuning), SQ_GEMM=0 keeps everything on cuBLASLt + sq_silu_mul.
+        mode = os.environ.get("SQ_GEMM", "auto")
         self.gemm = None
-        if os.environ.get("SQ_GEMM", "0") == "1":
-            self.gemm_err = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.gemm_err = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.lm_plan = None
+        stream_sized = h >= 2048
+        if mode == "1":
             self.gemm = []
             for ly in self.layers:
                 self.gemm.append(dict(qkv=self._plan(self.normed, ly["wqkv"], self.qkv),
                                       o=self._plan(self.attn_out, ly["wo"], self.proj),
-                                      gu=self._plan(self.normed, ly["wgu"], self.gate_up),
                                       d=self._plan(self.act, ly["wd"], self.proj)))
+        if mode in ("1", "auto") and stream_sized and self.I % 16 == 0:
+            for ly in self.layers:
+                wil = ops.interleave_gate_up(ly["wgu"][:self.I], ly["wgu"][self.I:])
+                ly["wgu_bytes"] = ly["wgu"].numel() * 2
+                ly["wgu"] = None                          # the plan's tiled copy is the only resident one
+                ly["gu_plan"] = ops.GemmPlan(self.normed, wil, self.act, self.gemm_err, tiled=True, swiglu=True)
+                del wil
+            self.lm_plan = ops.GemmPlan(self.normed, self.lm_head, self.logits, self.gemm_err, tiled=True)
+            self.lm_head_bytes = self.lm_head.numel() * 2
+            self.lm_head = None
         self.peer = None
         if self.tp.size > 1 and os.environ.get("SQ_TP_MODE", "fused") == "fused":
             from .peer import PeerBuffers
@@ -301,7 +314,16 @@ class LlamaRunner:
         try:
             return ops.GemmPlan(a, w, c, self.gemm_err)
         except Exception:
-            return None                                   # shape outside the kernel's tiling (K % 64, N % 128): cuBLASLt
+            return None                                   # shape outside the kernel's tiling (K % 64, N % 32): cuBLASLt
+
+    def _gate_up_act(self, ly, n: int):
+        """act[:n] = silu(normed[:n] @ Wg.T) * (normed[:n] @ Wu.T)   (Engine/Llama_modules.py:272)"""
+        plan = ly.get("gu_plan")
+        if plan is not None:
+            plan.run(n)
+            return
+        torch.mm(self.normed[:n], ly["wgu"].t(), out=self.gate_up[:n])
+        ops.silu_mul(self.gate_up, self.act, n)
 
     def _linear(self, l: int, key: str, x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, n: int):
         """out[:n] = x[:n] @ w.T"""
@@ -313,10 +335,11 @@ class LlamaRunner:
         torch.mm(x[:n], w.t(), out=out[:n])
 
     def weight_bytes(self) -> int:
-        b = self.embed.numel() + self.lm_head.numel() + self.norm.numel()
+        b = 2 * (self.embed.numel() + self.norm.numel()) + (self.lm_head.numel() * 2 if self.lm_head is not None else self.lm_head_bytes)
         for ly in self.layers:
-            b += sum(ly[k].numel() for k in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2"))
-        return 2 * b
+            b += 2 * sum(ly[k].numel() for k in ("wqkv", "wo", "wd", "ln1", "ln2"))
+            b += ly["wgu"].numel() * 2 if ly["wgu"] is not None else ly["wgu_bytes"]
+        return b
 
     @torch.no_grad()
     def forward(self, n: int, tokens: torch.Tensor, position_ids: torch.Tensor, storage_ids: torch.Tensor, *,
@@ -335,7 +358,7 @@ class LlamaRunner:
             self._prefetch_join()
             self._linear(l, "qkv", self.normed, ly["wqkv"], self.qkv, n)
             if self.pf_budget is not None:          # window A: RoPE + attention
-                self._prefetch(0, [(ly["wo"], 0), (ly["wgu"], 0)])
+                self._prefetch(0, [(ly["wo"], 0)] + ([(ly["wgu"], 0)] if ly["wgu"] is not None else []))
             ops.rope_kv_append(self.qkv, H, Hkv, D, self.cos, self.sin, position_ids, storage_ids, n,
                                self.k_cache[l], self.v_cache[l], M, state=state, n0=n0)
             ops.tree_attn(self.plan, l, n, state=state, n0=n0, kv_end=kv_end, prefix_len=prefix_len,
@@ -345,8 +368,7 @@ class LlamaRunner:
             if self.peer is not None:
                 torch.mm(self.attn_out[:n], ly["wo"].t(), out=self.peer.buf[0][:n])
                 self.peer.allreduce_add_rmsnorm(0, self.hidden, ly["ln2"], self.normed, n, self.eps)
-                torch.mm(nrm, ly["wgu"].t(), out=self.gate_up[:n])
-                ops.silu_mul(self.gate_up, self.act, n)
+                self._gate_up_act(ly, n)
                 torch.mm(self.act[:n], ly["wd"].t(), out=self.peer.buf[1][:n])
                 self.peer.allreduce_add_rmsnorm(1, self.hidden, nxt, self.normed, n, self.eps)
                 continue
@@ -354,20 +376,18 @@ class LlamaRunner:
             self._linear(l, "o", self.attn_out, ly["wo"], self.proj, n)
             if self.pf_budget is not None:          # window B: residual + RMSNorm; continue gate_up where window A stopped
                 wo_b = ly["wo"].numel() * 2
-                done = 0 if self.pf_budget[0] <= wo_b else \
-                    min(((self.pf_budget[0] - wo_b) // (ly["wgu"].shape[0] * 2)) // 64 * 64, ly["wgu"].shape[1])
-                self._prefetch(1, [(ly["wgu"], done)])
+                if ly["wgu"] is not None:
+                    done = 0 if self.pf_budget[0] <= wo_b else \
+                        min(((self.pf_budget[0] - wo_b) // (ly["wgu"].shape[0] * 2)) // 64 * 64, ly["wgu"].shape[1])
+                    self._prefetch(1, [(ly["wgu"], done)])
             self.tp.all_reduce(self.proj[:n])
             ops.add_rmsnorm(self.hidden, self.proj, ly["ln2"], self.normed, n, self.eps)
             self._prefetch_join()
-            self._linear(l, "gu", self.normed, ly["wgu"], self.gate_up, n)
-            if self.pf_budget is not None:          # window C: SiLU*up
-                self._prefetch(2, [(ly["wd"], 0)])
-            ops.silu_mul(self.gate_up, self.act, n)
+            self._gate_up_act(ly, n)
             self._prefetch_join()
             self._linear(l, "d", self.act, ly["wd"], self.proj, n)
             if self.pf_budget is not None:          # window D: residual + RMSNorm before the next layer's qkv / lm_head
-                nw = self.layers[l + 1]["wqkv"] if l + 1 < self.L else (None if skip_lm_head else self.lm_head)
+                nw = self.layers[l + 1]["wqkv"] if l + 1 < self.L else (None if skip_lm_head else self.lm_head)   # (None when tiled)
                 if nw is not None:
                     self._prefetch(3, [(nw, 0)])
             self.tp.all_reduce(self.proj[:n])
@@ -378,5 +398,8 @@ class LlamaRunner:
         self._prefetch_join()
         m = n - logits_from
         out = logits_out if logits_out is not None else self.logits[:m]
-        torch.mm(self.normed[logits_from:n], self.lm_head.t(), out=out)
+        if self.lm_plan is not None and out.stride(-1) == 1 and out.stride(0) % 8 == 0 and out.data_ptr() % 16 == 0:
+            self.lm_plan.run(m, a_row0=logits_from, out=out)
+        else:
+            torch.mm(self.normed[logits_from:n], self.lm_head.t(), out=out)
         return out

@@ -187,14 +187,59 @@ def l2_prefetch(w: torch.Tensor, col_from: int, col_to: int):
                                      stream_ptr()), "sq_l2_prefetch")
 
 
-class GemmPlan:
-    """C[:n] = A[:n] @ W.T for n <= 128 on the weight-streaming tcgen05 kernel (csrc/sq_gemm.cu)."""
+def gemm_pick_tiles(N: int, K: int):
+    bn, sp, mc = C.c_int(), C.c_int(), C.c_int()
+    check(_lib.load().sq_gemm_pick_tiles(N, K, C.byref(bn), C.byref(sp), C.byref(mc)), "sq_gemm_pick_tiles")
+    return bn.value, sp.value, mc.value
 
-    def __init__(self, a: torch.Tensor, w: torch.Tensor, c: torch.Tensor, err_flag: Optional[torch.Tensor] = None):
+
+def tile_weights(w: torch.Tensor) -> torch.Tensor:
+    """(N, K) row-major -> (ceil(N/BN), K/64, BN, 64) contiguous, rows beyond N zero (BN = the plan's tile width)."""
+    N, K = w.shape
+    bn, _, _ = gemm_pick_tiles(N, K)
+    tiles = (N + bn - 1) // bn
+    if tiles * bn != N:
+        pad = torch.zeros(tiles * bn, K, dtype=w.dtype, device=w.device)
+        pad[:N] = w
+        w = pad
+    return w.view(tiles, bn, K // 64, 64).permute(0, 2, 1, 3).contiguous()
+
+
+def interleave_gate_up(wg: torch.Tensor, wu: torch.Tensor) -> torch.Tensor:
+    """(I, K) gate and up weights -> (2I, K) with rows 32b..32b+15 = gate[16b..], rows 32b+16..32b+31 = up[16b..]: the
+    row order the fused SwiGLU epilogue of sq_gemm expects."""
+    I, K = wg.shape
+    assert I % 16 == 0 and wu.shape == wg.shape
+    return torch.stack([wg.reshape(I // 16, 16, K), wu.reshape(I // 16, 16, K)], dim=1).reshape(2 * I, K).contiguous()
+
+
+class GemmPlan:
+    """C[:n] = A[:n] @ W.T on the weight-streaming tcgen05 kernel (csrc/sq_gemm.cu); n > 128 runs one launch per 128 rows."""
+
+    def __init__(self, a: torch.Tensor, w: torch.Tensor, c: torch.Tensor, err_flag: Optional[torch.Tensor] = None,
+                 tiled: bool = False, swiglu: bool = False):
+        """tiled=True: `w` (N, K) is re-laid out once into the plan's own HBM-friendly copy (`self.w_tiled`, tile (n-tile,
+        k-block) = one contiguous BN x 64 block) and the plan streams that copy.
+        swiglu=True: `w` = interleave_gate_up(gate, up); the output (n, N/2) is silu(gate) * up (fused epilogue)."""
         lib = _lib.load()
         assert a.dtype == F16 and w.dtype == F16 and c.dtype == F16 and w.is_contiguous()
-        assert a.stride(-1) == 1 and c.stride(-1) == 1 and a.shape[1] == w.shape[1] and c.shape[1] >= w.shape[0]
+        assert a.stride(-1) == 1 and c.stride(-1) == 1 and a.shape[1] == w.shape[1]
+        assert c.shape[1] >= (w.shape[0] // 2 if swiglu else w.shape[0])
         self.handle = C.c_void_p()
+        self.w_tiled = None
+        self.N, self.K, self.swiglu = w.shape[0], w.shape[1], swiglu
+        self._create(lib, a, w, c, err_flag, tiled)
+        if swiglu:
+            check(lib.sq_gemm_plan_set_epilogue(self.handle, 1, w.shape[0] // 2), "sq_gemm_plan_set_epilogue")
+
+    def _create(self, lib, a, w, c, err_flag, tiled):
+        if tiled:
+            self.w_tiled = tile_weights(w)
+            self._keep = (a, self.w_tiled, c, err_flag)
+            check(lib.sq_gemm_plan_create_tiled(C.byref(self.handle), ptr(a), a.stride(0), a.shape[0], ptr(self.w_tiled),
+                                                w.shape[0], w.shape[1], ptr(c), c.stride(0), ptr(err_flag)),
+                  "sq_gemm_plan_create_tiled")
+            return
         self._keep = (a, w, c, err_flag)
         check(lib.sq_gemm_plan_create(C.byref(self.handle), ptr(a), a.stride(0), a.shape[0], ptr(w), w.shape[0], w.shape[1],
                                       ptr(c), c.stride(0), ptr(err_flag)), "sq_gemm_plan_create")
@@ -204,8 +249,15 @@ class GemmPlan:
         _lib.load().sq_gemm_plan_info(self.handle, C.byref(bn), C.byref(sp), C.byref(st))
         return bn.value, sp.value, st.value
 
-    def run(self, n: int):
-        check(_lib.load().sq_gemm_run(self.handle, n, stream_ptr()), "sq_gemm_run")
+    def run(self, n: int, a_row0: int = 0, out: Optional[torch.Tensor] = None):
+        """rows [a_row0, a_row0+n) of the activation buffer -> `out[:n]` (default: the plan's output buffer, same rows)."""
+        if a_row0 == 0 and out is None:
+            check(_lib.load().sq_gemm_run(self.handle, n, stream_ptr()), "sq_gemm_run")
+            return
+        if out is not None:
+            assert out.dtype == F16 and out.stride(-1) == 1 and out.shape[0] >= n
+        check(_lib.load().sq_gemm_run_at(self.handle, n, a_row0, ptr(out), out.stride(0) if out is not None else 0,
+                                         stream_ptr()), "sq_gemm_run_at")
 
     def __del__(self):
         try:

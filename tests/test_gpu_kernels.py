@@ -242,11 +242,22 @@ def test_top_p_filter_vs_torch_ops_on_device(rows, peaked, top_p, T):
     logits, _ = cases.sampling_case(40 + rows, rows, peaked)
     ref = _top_p_torch(logits.clone().to(DEV), top_p, T).cpu()
     got = ops().top_p_filter_(logits.clone().to(DEV), top_p, T).cpu()
-    d = _top_p_diff(got, ref)
-    # the kept set is a prefix of the (value, index)-sorted row; softmax's fp32 sum order can move one probability by an
-    # fp16 ulp and with it the cut by one token
-    assert int(d.max()) <= 1, d.tolist()
-    assert int((d > 0).sum()) <= max(1, rows // 4)
+    # The kept set is a prefix of the value-sorted row.  Two things are implementation-defined in the reference and may
+    # differ: WHICH members of the tie group the cut falls into survive (torch.sort leaves the order of equal logits
+    # open; the kernel keeps the lowest indices), and the cut may move by one token when softmax's fp32 sum order moves a
+    # probability by an fp16 ulp.  So: same number of survivors (+-1), and every differing position holds the boundary
+    # logit value (or there is a single differing position).
+    keep_g, keep_r = ~torch.isinf(got), ~torch.isinf(ref)
+    assert int((keep_g.sum(-1) - keep_r.sum(-1)).abs().max()) <= 1
+    shifted = 0
+    for r in range(rows):
+        diff = (keep_g[r] != keep_r[r]).nonzero().flatten()
+        if diff.numel() <= 1:
+            shifted += int(diff.numel())
+            continue
+        vals = logits[r][diff]                       # one tie group, or two adjacent ones when the cut also moved by one token
+        assert vals.unique().numel() <= 2, f"row {r}: differing survivors span more than the boundary tie groups: {vals.tolist()}"
+    assert shifted <= max(1, rows // 4)
     kept = (~torch.isinf(got)).sum(-1)
     assert bool((kept >= 1).all())                                     # the top token always survives
     if top_p == 0.0:
@@ -697,3 +708,64 @@ def test_weight_streaming_gemm_matches_cublas(N, K, n, expect):
     nbad, _ = ulp_close(c[:n], ref.to(F16), 1, atol=1e-3)
     assert nbad == 0, f"plan {plan.info()}: {nbad} outputs beyond 1 fp16 ulp of the fp32 product"
     assert (c[n:] == 7.0).all(), "rows >= n must not be written"
+
+
+@pytest.mark.parametrize("N,K,n,n_max,row0", [(1536, 512, 128, 128, 0), (6144, 768, 200, 256, 0), (22016, 4096, 100, 128, 0),
+                                              (32000, 768, 64, 320, 129), (1000 * 32, 1024, 257, 384, 3)])
+def test_weight_streaming_gemm_pretiled_row_tiles_and_offsets(N, K, n, n_max, row0):
+    """Pre-tiled weights ((n-tile, k-block) = one contiguous BN x 64 block of HBM), more than 128 rows (one launch per
+    128-row tile), and run-time activation-row offset + output override (the lm_head of a first verify: logits of the last
+    S rows into the tree's own buffer)."""
+    g = torch.Generator().manual_seed(N + K + n)
+    a = (torch.randn(n_max, K, generator=g) * 0.5).to(F16).to(DEV)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(F16).to(DEV)
+    c = torch.full((n_max, N), 7.0, dtype=F16, device=DEV)
+    err = torch.zeros(4, dtype=torch.int32, device=DEV)
+    plan = ops().GemmPlan(a, w, c, err, tiled=True)
+    ref = (a[row0:row0 + n].float() @ w.float().t()).to(F16)
+    if row0 == 0:
+        plan.run(n)
+        got, untouched = c[:n], c[n:]
+    else:
+        out = torch.full((n + 2, N), 7.0, dtype=F16, device=DEV)
+        plan.run(n, a_row0=row0, out=out)
+        got, untouched = out[:n], out[n:]
+        assert (c == 7.0).all(), "the plan's own buffer must not be written when an output override is given"
+    torch.cuda.synchronize()
+    assert err.tolist() == [0, 0, 0, 0], "GEMM pipeline watchdog fired"
+    nbad, _ = ulp_close(got, ref, 1, atol=1e-3)
+    assert nbad == 0, f"plan {plan.info()}: {nbad} outputs beyond 1 fp16 ulp of the fp32 product"
+    assert (untouched == 7.0).all(), "rows >= n must not be written"
+
+
+@pytest.mark.parametrize("I,K,n,tiled", [(3072, 768, 34, True), (11008, 4096, 128, True), (1376, 2048, 150, True), (3072, 768, 128, False)])
+def test_gemm_fused_swiglu_epilogue_bit_exact(I, K, n, tiled):
+    """gate_up GEMM with the SwiGLU epilogue fused (weights interleaved 16 gate | 16 up rows) against the unfused chain on
+    the same kernel: plain sq_gemm -> sq_silu_mul.  Same accumulators, same rounding points => bit-identical."""
+    g = torch.Generator().manual_seed(I + K)
+    n_max = 256 if n > 128 else 128
+    a = (torch.randn(n_max, K, generator=g) * 0.5).to(F16).to(DEV)
+    wg = (torch.randn(I, K, generator=g) * 0.05).to(F16).to(DEV)
+    wu = (torch.randn(I, K, generator=g) * 0.05).to(F16).to(DEV)
+    err = torch.zeros(4, dtype=torch.int32, device=DEV)
+    act = torch.full((n_max, I), 7.0, dtype=F16, device=DEV)
+    fused = ops().GemmPlan(a, ops().interleave_gate_up(wg, wu), act, err, tiled=tiled, swiglu=True)
+    fused.run(n)
+    gu = torch.zeros(n_max, 2 * I, dtype=F16, device=DEV)
+    plain = ops().GemmPlan(a, torch.cat([wg, wu], 0).contiguous(), gu, err)
+    plain.run(n)
+    want = torch.zeros(n_max, I, dtype=F16, device=DEV)
+    ops().silu_mul(gu, want, n)
+    torch.cuda.synchronize()
+    assert err.tolist() == [0, 0, 0, 0]
+    # same tile shape => same accumulation order => bit-identical; a different BN can only move the fp32 sum by an ulp
+    same_tiles = fused.info()[0] == plain.info()[0]
+    if same_tiles:
+        assert torch.equal(act[:n], want[:n])
+    else:
+        nbad, _ = ulp_close(act[:n], want[:n], 2, atol=1e-4)
+        assert nbad <= act[:n].numel() * 1e-3
+    ref = torch.nn.functional.silu((a[:n].float() @ wg.float().t()).to(F16).float()).to(F16) * (a[:n].float() @ wu.float().t()).to(F16)
+    nbad, _ = ulp_close(act[:n], ref, 2, atol=1e-3)
+    assert nbad <= act[:n].numel() * 1e-3, f"{nbad} outputs beyond 2 ulp of the torch chain"
+    assert (act[n:] == 7.0).all()

@@ -18,7 +18,7 @@ for name, (N, K) in shapes.items():
     a = (torch.randn(128, K, device=dev) * 0.5).half()
     ws = [(torch.randn(N, K, device=dev) * 0.05).half() for _ in range(COPIES)]
     c = torch.zeros(128, N, device=dev, dtype=torch.float16)
-    plans = [ops.GemmPlan(a, w, c, err) for w in ws]
+    plans = [ops.GemmPlan(a, w, c, err, tiled=os.environ.get('PROBE_TILED', '0') == '1') for w in ws]
     plans[0].run(n)
     torch.cuda.synchronize()
     ref = (a[:n].float() @ ws[0].float().t())
