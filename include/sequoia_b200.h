@@ -199,8 +199,15 @@ int sq_l2_prefetch(const void* base, int64_t pitch_bytes, int rows, int64_t off_
 typedef struct sq_gemm_plan sq_gemm_plan;
 int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N, int K,
                         sq_half* c, int ldc, int* err_flag);
+#define SQ_GEMM_TILED 1
+#define SQ_GEMM_SWIGLU 2
 /* Tile shape (BN, K splits, multicast width) a plan for (N, K) will use -- needed to pre-tile weights. */
 int sq_gemm_pick_tiles(int N, int K, int* bn, int* split, int* mc);
+int sq_gemm_pick_tiles_ex(int N, int K, int flags, int* bn, int* split, int* mc);
+/* sq_gemm_plan_create with flags: SQ_GEMM_TILED (w = the pre-tiled copy) | SQ_GEMM_SWIGLU (fused SwiGLU epilogue, n_out = N/2;
+ * excludes split-K tiles). */
+int sq_gemm_plan_create_ex(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N, int K,
+                           sq_half* c, int ldc, int* err_flag, int flags);
 /* As sq_gemm_plan_create, for weights stored pre-tiled as (ceil(N/BN), K/64, BN, 64) fp16 contiguous (rows beyond N
  * zero): every weight TMA load is one contiguous BN*128-byte block of HBM. */
 int sq_gemm_plan_create_tiled(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w_tiled, int N, int K,

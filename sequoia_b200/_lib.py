@@ -47,6 +47,8 @@ _SIGNATURES = {
     "sq_l2_prefetch": (i32, [vp, i64, i32, i64, i64, vp]),
     "sq_gemm_plan_create": (i32, [C.POINTER(vp), vp, i32, i32, vp, i32, i32, vp, i32, vp]),
     "sq_gemm_pick_tiles": (i32, [i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "sq_gemm_pick_tiles_ex": (i32, [i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "sq_gemm_plan_create_ex": (i32, [C.POINTER(vp), vp, i32, i32, vp, i32, i32, vp, i32, vp, i32]),
     "sq_gemm_plan_create_tiled": (i32, [C.POINTER(vp), vp, i32, i32, vp, i32, i32, vp, i32, vp]),
     "sq_gemm_plan_set_epilogue": (i32, [vp, i32, i32]),
     "sq_gemm_plan_destroy": (i32, [vp]),

@@ -279,7 +279,7 @@ static int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t
 // Tile selection: put a CTA on (nearly) every SM with the widest N tile that allows -- per-SM ingest, not HBM, is what
 // limits a 128-row weight stream, and the activation tile every CTA re-reads is pure overhead: a wider BN and a 2-CTA
 // multicast of the activation slab both raise the weight share of each SM's ingest.
-static void choose_tiles(sq_gemm_plan* p) {
+static void choose_tiles(sq_gemm_plan* p, bool allow_split) {
   const int N = p->N, kb = p->K / 64;
   const int cands[] = {256, 224, 192, 160, 128, 96, 64};
   int best_bn = 128, best_split = 1, best_mc = 1;
@@ -287,7 +287,7 @@ static void choose_tiles(sq_gemm_plan* p) {
   for (int bn : cands) {
     const int tiles = (N + bn - 1) / bn;
     for (int split : {1, 2, 4}) {
-      if (kb % split) continue;
+      if (kb % split || (split > 1 && !allow_split)) continue;
       if (split > 1 && (bn > 128 || N % bn)) continue;       // DSMEM reduction buffers: BN <= 128, no ragged tile
       const int ctas = tiles * split;
       if (ctas > 148) continue;
@@ -306,31 +306,34 @@ static void choose_tiles(sq_gemm_plan* p) {
 
 static void pick_tiles(sq_gemm_plan* p) {
   const int kb = p->K / 64;
-  choose_tiles(p);
+  const bool allow_split = p->epi == 0;                 // a fused epilogue needs the whole K sum in one CTA
+  choose_tiles(p, allow_split);
   const char* force = getenv("SQ_GEMM_FORCE");          // tuning / debugging: "bn,split,mc"
   if (force) {
     int fb = 0, fs = 0, fm = 1;
     const int nf = sscanf(force, "%d,%d,%d", &fb, &fs, &fm);
     const bool bn_ok = fb == 64 || fb == 96 || fb == 128 || fb == 160 || fb == 192 || fb == 224 || fb == 256;
     if (nf >= 2 && bn_ok && (fs == 1 || fs == 2 || fs == 4) && kb % fs == 0 && (fm == 1 || fm == 2) &&
-        !(fs > 1 && (fb > 128 || p->N % fb)) && !(fm == 2 && ((p->N + fb - 1) / fb) % 2)) {
+        !(fs > 1 && (fb > 128 || p->N % fb || !allow_split)) && !(fm == 2 && ((p->N + fb - 1) / fb) % 2)) {
       p->bn = fb; p->split = fs; p->mc = fm;
     }
   }
 }
 
 /* The tile shape a plan for (N, K) will use: callers that pre-tile the weights need BN before they build the copy. */
-extern "C" int sq_gemm_pick_tiles(int N, int K, int* bn, int* split, int* mc) {
+extern "C" int sq_gemm_pick_tiles(int N, int K, int* bn, int* split, int* mc) { return sq_gemm_pick_tiles_ex(N, K, 0, bn, split, mc); }
+
+extern "C" int sq_gemm_pick_tiles_ex(int N, int K, int flags, int* bn, int* split, int* mc) {
   SQ_CHECK_ARG(K % 64 == 0 && N % 32 == 0, "sq_gemm_pick_tiles: K %% 64, N %% 32");
   sq_gemm_plan p{};
-  p.N = N; p.K = K;
+  p.N = N; p.K = K; p.epi = (flags & SQ_GEMM_SWIGLU) ? 1 : 0;
   pick_tiles(&p);
   *bn = p.bn; *split = p.split; *mc = p.mc;
   return SQ_OK;
 }
 
 static int plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N, int K, sq_half* c,
-                       int ldc, int* err_flag, int tiled);
+                       int ldc, int* err_flag, int flags);
 
 extern "C" int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N,
                                    int K, sq_half* c, int ldc, int* err_flag) {
@@ -342,16 +345,25 @@ extern "C" int sq_gemm_plan_create(sq_gemm_plan** plan, const sq_half* a, int ld
  * 128-byte segments K*2 bytes apart. */
 extern "C" int sq_gemm_plan_create_tiled(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w_tiled,
                                          int N, int K, sq_half* c, int ldc, int* err_flag) {
-  return plan_create(plan, a, lda, n_max, w_tiled, N, K, c, ldc, err_flag, 1);
+  return plan_create(plan, a, lda, n_max, w_tiled, N, K, c, ldc, err_flag, SQ_GEMM_TILED);
+}
+
+/* flags: SQ_GEMM_TILED (weights pre-tiled as above) | SQ_GEMM_SWIGLU (fused epilogue, see sq_gemm_plan_set_epilogue; the
+ * tile choice then excludes split-K) */
+extern "C" int sq_gemm_plan_create_ex(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N,
+                                      int K, sq_half* c, int ldc, int* err_flag, int flags) {
+  return plan_create(plan, a, lda, n_max, w, N, K, c, ldc, err_flag, flags);
 }
 
 static int plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max, const sq_half* w, int N, int K, sq_half* c,
-                       int ldc, int* err_flag, int tiled) {
+                       int ldc, int* err_flag, int flags) {
+  const int tiled = (flags & SQ_GEMM_TILED) ? 1 : 0;
   SQ_CHECK_ARG(plan && a && w && c, "sq_gemm_plan_create: null pointer");
   SQ_CHECK_ARG(K % 64 == 0 && N % 32 == 0 && lda % 8 == 0 && ldc % 8 == 0, "sq_gemm_plan_create: K %% 64, N %% 32");
   sq_gemm_plan* p = new sq_gemm_plan();
   p->c = (__half*)c; p->ldc = ldc; p->n_max = n_max; p->N = N; p->K = K; p->err_flag = err_flag;
-  p->tiled = tiled; p->epi = 0; p->n_out = 0;
+  p->tiled = tiled; p->epi = (flags & SQ_GEMM_SWIGLU) ? 1 : 0; p->n_out = p->epi ? N / 2 : 0;
+  if (p->epi) SQ_CHECK_ARG(N % 32 == 0, "sq_gemm_plan_create: SwiGLU needs N %% 32 == 0");
   pick_tiles(p);
   {
     const char* pe = getenv("SQ_PDL");

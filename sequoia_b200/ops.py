@@ -187,16 +187,19 @@ def l2_prefetch(w: torch.Tensor, col_from: int, col_to: int):
                                      stream_ptr()), "sq_l2_prefetch")
 
 
-def gemm_pick_tiles(N: int, K: int):
+GEMM_TILED, GEMM_SWIGLU = 1, 2          # sq_gemm_plan_create_ex flags (include/sequoia_b200.h)
+
+
+def gemm_pick_tiles(N: int, K: int, flags: int = 0):
     bn, sp, mc = C.c_int(), C.c_int(), C.c_int()
-    check(_lib.load().sq_gemm_pick_tiles(N, K, C.byref(bn), C.byref(sp), C.byref(mc)), "sq_gemm_pick_tiles")
+    check(_lib.load().sq_gemm_pick_tiles_ex(N, K, flags, C.byref(bn), C.byref(sp), C.byref(mc)), "sq_gemm_pick_tiles_ex")
     return bn.value, sp.value, mc.value
 
 
-def tile_weights(w: torch.Tensor) -> torch.Tensor:
+def tile_weights(w: torch.Tensor, flags: int = 0) -> torch.Tensor:
     """(N, K) row-major -> (ceil(N/BN), K/64, BN, 64) contiguous, rows beyond N zero (BN = the plan's tile width)."""
     N, K = w.shape
-    bn, _, _ = gemm_pick_tiles(N, K)
+    bn, _, _ = gemm_pick_tiles(N, K, flags)
     tiles = (N + bn - 1) // bn
     if tiles * bn != N:
         pad = torch.zeros(tiles * bn, K, dtype=w.dtype, device=w.device)
@@ -228,21 +231,12 @@ class GemmPlan:
         self.handle = C.c_void_p()
         self.w_tiled = None
         self.N, self.K, self.swiglu = w.shape[0], w.shape[1], swiglu
-        self._create(lib, a, w, c, err_flag, tiled)
-        if swiglu:
-            check(lib.sq_gemm_plan_set_epilogue(self.handle, 1, w.shape[0] // 2), "sq_gemm_plan_set_epilogue")
-
-    def _create(self, lib, a, w, c, err_flag, tiled):
+        flags = (GEMM_TILED if tiled else 0) | (GEMM_SWIGLU if swiglu else 0)
         if tiled:
-            self.w_tiled = tile_weights(w)
-            self._keep = (a, self.w_tiled, c, err_flag)
-            check(lib.sq_gemm_plan_create_tiled(C.byref(self.handle), ptr(a), a.stride(0), a.shape[0], ptr(self.w_tiled),
-                                                w.shape[0], w.shape[1], ptr(c), c.stride(0), ptr(err_flag)),
-                  "sq_gemm_plan_create_tiled")
-            return
+            self.w_tiled = w = tile_weights(w, flags)
         self._keep = (a, w, c, err_flag)
-        check(lib.sq_gemm_plan_create(C.byref(self.handle), ptr(a), a.stride(0), a.shape[0], ptr(w), w.shape[0], w.shape[1],
-                                      ptr(c), c.stride(0), ptr(err_flag)), "sq_gemm_plan_create")
+        check(lib.sq_gemm_plan_create_ex(C.byref(self.handle), ptr(a), a.stride(0), a.shape[0], ptr(w), self.N, self.K,
+                                         ptr(c), c.stride(0), ptr(err_flag), flags), "sq_gemm_plan_create_ex")
 
     def info(self):
         bn, sp, st = C.c_int(), C.c_int(), C.c_int()
