@@ -693,8 +693,7 @@ extern "C" int sq_attn_plan_create(sq_attn_plan** plan, const sq_half* q, int ld
   {
     const int G = H / Hkv;
     p->GP = (G <= TILE_Q && TILE_Q % G == 0) ? G : 1;
-    const char* pe = getenv("SQ_PDL");
-    p->pdl = (pe && atoi(pe)) ? 1 : 0;
+    p->pdl = pdl_enabled() ? 1 : 0;
   }
   p->err_flag = (int*)workspace;
   {

@@ -19,8 +19,8 @@ void set_error(const char* fmt, ...) {
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("SQ_PDL");
-    v = (e && atoi(e)) ? 1 : 0;
+    const char* e = getenv("SQ_PDL");           // programmatic dependent launch: on by default, SQ_PDL=0 turns it off
+    v = (e && !atoi(e)) ? 0 : 1;
   }
   return v == 1;
 }

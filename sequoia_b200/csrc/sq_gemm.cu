@@ -366,8 +366,7 @@ static int plan_create(sq_gemm_plan** plan, const sq_half* a, int lda, int n_max
   if (p->epi) SQ_CHECK_ARG(N % 32 == 0, "sq_gemm_plan_create: SwiGLU needs N %% 32 == 0");
   pick_tiles(p);
   {
-    const char* pe = getenv("SQ_PDL");
-    p->pdl = (pe && atoi(pe)) ? 1 : 0;
+    p->pdl = pdl_enabled() ? 1 : 0;
   }
   p->stages = p->split > 1 ? 4 : (p->bn >= 224 ? 4 : p->bn >= 160 ? 5 : p->bn >= 96 ? 6 : 8);   // == the dispatch table below
   int rc = encode_2d(&p->tm_a, a, (uint64_t)K, (uint64_t)n_max, (uint64_t)lda * 2, 64, (uint32_t)(128 / p->mc),

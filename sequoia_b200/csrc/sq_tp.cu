@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(256) tp_allreduce_add_rmsnorm_kernel(TpArgs t,
                                                                        __half* __restrict__ out, int hidden, float eps) {
   __shared__ float red[8];
   const int r = blockIdx.x, tid = threadIdx.x;
+  pdl_wait();                                                // the row-parallel GEMM's partial is complete and visible
+  pdl_trigger();
   const uint32_t e = t.epoch[0] + 1;                         // identical in every CTA: only bumped by the last CTA
   if (r == 0 && tid < t.N && tid != t.rank) st_release_sys(t.flags[tid] + t.rank, e);   // "my partial is ready"
   if (tid < t.N && tid != t.rank) {                          // wait until every peer's partial of this epoch is ready
@@ -149,6 +151,8 @@ __global__ void __launch_bounds__(256) tp_allreduce2_add_rmsnorm_kernel(Tp2Args 
                                                                         __half* __restrict__ out, int n, int hidden, float eps) {
   __shared__ float red[8];
   const int tid = threadIdx.x, N = t.N, rank = t.rank;
+  pdl_wait();
+  pdl_trigger();
   // block -> row: owned rows (rank, rank+N, ...) first, then the others in order
   const int n_own = (n - rank + N - 1) / N;                  // rows r < n with r % N == rank   (n > rank assumed below)
   int r;
@@ -324,10 +328,10 @@ extern "C" int sq_tp_allreduce_add_rmsnorm(sq_half* resid, const void* const* ho
   t.N = N;
   cudaStream_t st = (cudaStream_t)stream;
   const int nvec = hidden / 8;
-  if (nvec <= 256) tp_allreduce_add_rmsnorm_kernel<1><<<n, 256, 0, st>>>(t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
-  else if (nvec <= 512) tp_allreduce_add_rmsnorm_kernel<2><<<n, 256, 0, st>>>(t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
-  else if (nvec <= 1024) tp_allreduce_add_rmsnorm_kernel<4><<<n, 256, 0, st>>>(t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
-  else tp_allreduce_add_rmsnorm_kernel<8><<<n, 256, 0, st>>>(t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
+  if (nvec <= 256) launch_k(tp_allreduce_add_rmsnorm_kernel<1>, dim3(n), dim3(256), 0, st, t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
+  else if (nvec <= 512) launch_k(tp_allreduce_add_rmsnorm_kernel<2>, dim3(n), dim3(256), 0, st, t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
+  else if (nvec <= 1024) launch_k(tp_allreduce_add_rmsnorm_kernel<4>, dim3(n), dim3(256), 0, st, t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
+  else launch_k(tp_allreduce_add_rmsnorm_kernel<8>, dim3(n), dim3(256), 0, st, t, (__half*)resid, (const __half*)weight, (__half*)out, hidden, eps);
   SQ_CHECK_LAUNCH("sq_tp_allreduce_add_rmsnorm");
   return SQ_OK;
 }
@@ -352,10 +356,10 @@ extern "C" int sq_tp_allreduce2_add_rmsnorm(sq_half* resid, const void* const* h
   cudaStream_t st = (cudaStream_t)stream;
   const int nvec = hidden / 8;
   __half* r = (__half*)resid; const __half* w = (const __half*)weight; __half* o = (__half*)out;
-  if (nvec <= 256) tp_allreduce2_add_rmsnorm_kernel<1><<<n, 256, 0, st>>>(t, r, w, o, n, hidden, eps);
-  else if (nvec <= 512) tp_allreduce2_add_rmsnorm_kernel<2><<<n, 256, 0, st>>>(t, r, w, o, n, hidden, eps);
-  else if (nvec <= 1024) tp_allreduce2_add_rmsnorm_kernel<4><<<n, 256, 0, st>>>(t, r, w, o, n, hidden, eps);
-  else tp_allreduce2_add_rmsnorm_kernel<8><<<n, 256, 0, st>>>(t, r, w, o, n, hidden, eps);
+  if (nvec <= 256) launch_k(tp_allreduce2_add_rmsnorm_kernel<1>, dim3(n), dim3(256), 0, st, t, r, w, o, n, hidden, eps);
+  else if (nvec <= 512) launch_k(tp_allreduce2_add_rmsnorm_kernel<2>, dim3(n), dim3(256), 0, st, t, r, w, o, n, hidden, eps);
+  else if (nvec <= 1024) launch_k(tp_allreduce2_add_rmsnorm_kernel<4>, dim3(n), dim3(256), 0, st, t, r, w, o, n, hidden, eps);
+  else launch_k(tp_allreduce2_add_rmsnorm_kernel<8>, dim3(n), dim3(256), 0, st, t, r, w, o, n, hidden, eps);
   SQ_CHECK_LAUNCH("sq_tp_allreduce2_add_rmsnorm");
   return SQ_OK;
 }
