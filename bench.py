@@ -361,6 +361,8 @@ def run_b200(args):
 
         h2d = 0
         d2h = 0
+        draft_ms = 0.0
+        verify_ms = 0.0
 
         def run_steps(self, k, timed, host=False):
             done = tokens = 0
@@ -374,8 +376,16 @@ def run_b200(args):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 while done < k and self.len < max_len and not self.terminate:
+                    ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    ea.record()
                     self.tree.construct_grow_map()
+                    eb.record()
                     valid, _, _, self.terminate = self.tree.verify()
+                    ec.record()
+                    ec.synchronize()
+                    if timed:                                         # phase split (tests/testbed.py:144-219 reports the same)
+                        self.draft_ms += ea.elapsed_time(eb)
+                        self.verify_ms += eb.elapsed_time(ec)
                     tokens += valid.shape[0] - self.len
                     self.len = valid.shape[0]
                     if int(self.tree.rt.host_state[5]) in (0, 2):       # bonus token is EOS / pad (testbed.py:87)
@@ -450,6 +460,9 @@ def run_b200(args):
                    "l2": "inputs larger than L2: each step streams the target's %.1f GB of weights" % (target.engine.runner.weight_bytes() / 1e9)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": extra,
         "wall_s_timed_region": round(wall, 3), "device_errors": dev_err,
+        "phases": {"draft_ms_per_step": round(loop.draft_ms / args.steps, 4), "verify_ms_per_step": round(loop.verify_ms / args.steps, 4),
+                   "note": "CUDA events around construct_grow_map() (draft tree, rank 0 only) and verify() (target forward over "
+                           "all ranks + accept walk + KV compaction + 1-token draft forward) of the timed steps"},
     }
     if tp_parity is not None:
         out["tp_parity"] = tp_parity

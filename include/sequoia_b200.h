@@ -248,6 +248,25 @@ int sq_tp_allreduce2_add_rmsnorm(sq_half* resid, const void* const* host_proj_pt
                                  void* const* host_flag_ptrs, void* const* host_rowflag_ptrs, uint32_t* epoch, int rank,
                                  int N, const sq_half* weight, sq_half* out, int n, int hidden, float eps, void* stream);
 
+/* ---- fused draft forward (csrc/sq_draft.cu): one persistent cooperative kernel per tree level for small draft models
+ * (Engine/Engine.py:158-164 replays a ~25-kernel graph per level; Tree/SpecTree.py:245-259).  Supported: head_dim 64,
+ * n_heads * 64 == hidden, no GQA, intermediate %% hidden == 0, <= 16 layers, max_length <= 512 (see sq_draft_supported).
+ * layer_weights: 6 pointers per layer {wqkv (3h,h), wo (h,h), wgu (2I,h), wd (h,I), input_layernorm, post_attention_layernorm}.
+ * workspace: sq_draft_workspace_bytes(hidden, intermediate) bytes of device memory owned by the caller. ---- */
+typedef struct sq_draft_plan sq_draft_plan;
+int64_t sq_draft_workspace_bytes(int hidden, int inter);
+int sq_draft_supported(int hidden, int inter, int n_layers, int n_heads, int n_kv_heads, int head_dim, int vocab, int max_length);
+int sq_draft_plan_create(sq_draft_plan** plan, int hidden, int inter, int n_layers, int n_heads, int vocab, int max_length,
+                         float eps, const sq_half* embed, const sq_half* const* layer_weights, const sq_half* final_norm,
+                         const sq_half* lm_head, const sq_half* cos, const sq_half* sin, sq_half* k_cache, sq_half* v_cache,
+                         void* workspace, int64_t workspace_bytes);
+int sq_draft_plan_destroy(sq_draft_plan* plan);
+/* Forward n (<= 64) rows = tree nodes [n0, n0+n) in tree-relative addressing (base = state[P]-1: tokens / positions / cache
+ * slots at base+n0+r; keys [0, base+kv_end) under the packed tree mask); appends their K/V, writes logits_out (n, V). */
+int sq_draft_forward(sq_draft_plan* plan, int n, const int64_t* tokens, const int64_t* position_ids, const int64_t* storage_ids,
+                     const int32_t* state, int n0, int kv_end, const uint32_t* tree_bits, int tree_words, int tree_size,
+                     sq_half* logits_out, int64_t ld_logits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,11 @@ _SIGNATURES = {
     "sq_tp_ipc_close": (i32, [vp]),
     "sq_tp_allreduce_add_rmsnorm": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp]),
     "sq_tp_allreduce2_add_rmsnorm": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp]),
+    "sq_draft_workspace_bytes": (i64, [i32, i32]),
+    "sq_draft_supported": (i32, [i32, i32, i32, i32, i32, i32, i32, i32]),
+    "sq_draft_plan_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64]),
+    "sq_draft_plan_destroy": (i32, [vp]),
+    "sq_draft_forward": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, i64, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -261,16 +261,29 @@ class LlamaRunner:
                 self.gemm.append(dict(qkv=self._plan(self.normed, ly["wqkv"], self.qkv),
                                       o=self._plan(self.attn_out, ly["wo"], self.proj),
                                       d=self._plan(self.act, ly["wd"], self.proj)))
-        if mode in ("1", "auto") and stream_sized and self.I % 16 == 0:
+        # (a fused-epilogue plan cannot split K, so a narrow shard -- TP-4/8 of a 7B -- would leave most SMs idle: those
+        # stay on cuBLASLt + sq_silu_mul; measured at TP-4: 4.15 ms / step with the plan vs 3.4 ms without)
+        gu_bn, gu_split, _ = ops.gemm_pick_tiles(2 * self.I, h, ops.GEMM_SWIGLU) if self.I % 16 == 0 and h % 64 == 0 else (0, 1, 1)
+        gu_ctas = (-(-2 * self.I // gu_bn)) * gu_split if gu_bn else 0
+        if mode in ("1", "auto") and stream_sized and gu_ctas >= 120:
             for ly in self.layers:
                 wil = ops.interleave_gate_up(ly["wgu"][:self.I], ly["wgu"][self.I:])
                 ly["wgu_bytes"] = ly["wgu"].numel() * 2
                 ly["wgu"] = None                          # the plan's tiled copy is the only resident one
                 ly["gu_plan"] = ops.GemmPlan(self.normed, wil, self.act, self.gemm_err, tiled=True, swiglu=True)
                 del wil
+        if mode in ("1", "auto") and stream_sized and V % 32 == 0 and h % 64 == 0:
             self.lm_plan = ops.GemmPlan(self.normed, self.lm_head, self.logits, self.gemm_err, tiled=True)
             self.lm_head_bytes = self.lm_head.numel() * 2
             self.lm_head = None
+        # Small draft models: one persistent cooperative kernel per tree level instead of ~25 launches (csrc/sq_draft.cu);
+        # tree-relative forwards of <= 64 rows take it, everything else (prefill, dense-mask API) the multi-kernel path.
+        # SQ_DRAFT_FUSED=0 turns it off.
+        self.draft_plan = None
+        if (os.environ.get("SQ_DRAFT_FUSED", "1") != "0" and tp == 1 and self.layers[0]["wgu"] is not None and
+                ops.draft_supported(h, self.I, self.L, self.H, self.Hkv, D, V, max_length)):
+            self.draft_plan = ops.DraftPlan(h, self.I, self.H, V, max_length, self.eps, self.embed, self.layers, self.norm,
+                                            self.lm_head, self.cos, self.sin, self.k_cache, self.v_cache)
         self.peer = None
         if self.tp.size > 1 and os.environ.get("SQ_TP_MODE", "fused") == "fused":
             from .peer import PeerBuffers
@@ -351,6 +364,12 @@ class LlamaRunner:
         Logits of rows [logits_from, n) are written to `logits_out` (default: the internal buffer) and returned."""
         assert 0 < n <= self.n_max
         H, Hkv, D, M = self.H, self.Hkv, self.D, self.M
+        if (self.draft_plan is not None and state is not None and n <= ops.DraftPlan.MAX_ROWS and dense_mask is None
+                and logits_from == 0 and not skip_lm_head and self.attn_impl == 0):
+            out = logits_out if logits_out is not None else self.logits[:n]
+            self.draft_plan.forward(n, tokens, position_ids, storage_ids, state, n0, kv_end, tree_bits, tree_words,
+                                    tree_size, out)
+            return out
         hid, nrm = self.hidden[:n], self.normed[:n]
         ops.embed_rows(self.embed, tokens, n, self.hidden, state=state, n0=n0)
         ops.rmsnorm(self.hidden, self.layers[0]["ln1"], self.normed, n, self.eps)

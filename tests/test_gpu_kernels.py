@@ -769,3 +769,66 @@ def test_gemm_fused_swiglu_epilogue_bit_exact(I, K, n, tiled):
     nbad, _ = ulp_close(act[:n], ref, 2, atol=1e-3)
     assert nbad <= act[:n].numel() * 1e-3, f"{nbad} outputs beyond 2 ulp of the torch chain"
     assert (act[n:] == 7.0).all()
+
+
+# ------------------------------------------------------------------------------------------------ fused draft forward
+@pytest.mark.parametrize("hidden,inter,heads,layers,M", [(768, 3072, 12, 2, 384), (512, 1024, 8, 3, 256)])
+def test_fused_draft_forward_matches_multi_kernel_path(hidden, inter, heads, layers, M):
+    """csrc/sq_draft.cu (one persistent cooperative kernel per tree level) against the multi-kernel forward of the same
+    LlamaRunner weights: same prefill, then every level of the 128-node config-2 tree, a 1-row forward (the bonus token of
+    prepare_for_next_iter) and a 64-row level.  Logits within 2e-3 of the row's max |logit| (different GEMM tiling /
+    attention reduction order, same fp16 rounding points), appended K/V rows within 2 fp16 ulp."""
+    from sequoia_b200.model import LlamaRunner
+    from sequoia_b200.tree import pack_tree_mask
+    cfg = O.LlamaCfg(hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers, num_attention_heads=heads,
+                     num_key_value_heads=heads, vocab_size=cases.V)
+    w = O.init_llama_weights(cfg, 4242)
+    spec = {"config": cfg, "state_dict": w}
+    os.environ["SQ_DRAFT_FUSED"] = "0"
+    try:
+        ref = LlamaRunner(spec, M, device=DEV)
+    finally:
+        os.environ.pop("SQ_DRAFT_FUSED", None)
+    fused = LlamaRunner(spec, M, device=DEV)
+    assert ref.draft_plan is None and fused.draft_plan is not None, "the fused draft kernel must engage for this shape"
+    gm = cases.load_growmap("A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt")
+    S = gm["size"]
+    P = 96
+    g = torch.Generator().manual_seed(7)
+    tokens = torch.randint(3, cases.V, (M,), generator=g).to(DEV)
+    pos = torch.zeros(M, dtype=torch.long)
+    pos[:P] = torch.arange(P)
+    pos[P:P + S - 1] = gm["depth"][1:] + P - 1
+    pos = pos.to(DEV)
+    sto = torch.arange(M, device=DEV)
+    state = torch.zeros(16, dtype=torch.int32, device=DEV)
+    state[0] = P
+    bits = pack_tree_mask(gm["mask"]).to(DEV)
+    kw = dict(tree_bits=bits, tree_words=bits.shape[1], tree_size=S)
+    for rn in (ref, fused):          # causal prefill of the P prompt rows (multi-kernel path in both: state=None)
+        rn.forward(P, tokens, pos, sto, state=None, n0=0, kv_end=P, prefix_len=P, logits_from=P - 1)
+    assert torch.equal(ref.k_cache, fused.k_cache)
+    levels = []
+    first = 1
+    for br in gm["branches"][:-1]:
+        tb = int(sum(br))
+        levels.append((first, tb))
+        first += tb
+    levels = [(0, 1)] + levels + [(1, 64)]           # root row alone (bonus-token forward), tree levels, a 64-row batch
+    worst = 0.0
+    for n0, n in levels:
+        la = torch.zeros(n, cases.V, dtype=F16, device=DEV)
+        lb = torch.zeros(n, cases.V, dtype=F16, device=DEV)
+        ref.forward(n, tokens, pos, sto, state=state, n0=n0, kv_end=n0 + n, logits_out=la, **kw)
+        fused.forward(n, tokens, pos, sto, state=state, n0=n0, kv_end=n0 + n, logits_out=lb, **kw)
+        torch.cuda.synchronize()
+        scale = la.float().abs().amax(dim=-1, keepdim=True)
+        rel = ((la.float() - lb.float()).abs() / scale).max().item()
+        worst = max(worst, rel)
+        assert rel < 2e-3, f"level n0={n0} n={n}: fused draft logits differ by {rel:.3e}"
+        sl = slice(P - 1 + n0, P - 1 + n0 + n)
+        for ca, cb in ((ref.k_cache, fused.k_cache), (ref.v_cache, fused.v_cache)):
+            nbad, _ = ulp_close(ca[:, :, :, sl], cb[:, :, :, sl], 2, atol=2e-4)
+            assert nbad <= ca[:, :, :, sl].numel() * 2e-3, f"level n0={n0}: {nbad} appended K/V values beyond 2 ulp"
+    with open(os.path.join(os.path.dirname(G), "..", "gpurun_out", "logit_err.log"), "a") as f:
+        f.write(f"fused draft forward (h={hidden} I={inter} L={layers}): max rel logit diff vs the multi-kernel path {worst:.3e}\n")
