@@ -412,7 +412,16 @@ def run_b200(args):
     sampler.start()
     barrier()
     t_wall0 = time.time()
-    tokens, ms = loop.run_steps(args.steps, timed=True)
+    if args.timeline:
+        # in-process CUPTI trace of the timed steps (no kernel replay, so it works under tensor parallelism where ncu cannot):
+        # per-kernel device time as it runs INSIDE the graphs.  A run with --timeline is a diagnosis, not a bench value.
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            tokens, ms = loop.run_steps(args.steps, timed=True)
+            torch.cuda.synchronize()
+        write_timeline(prof, args.timeline, args.steps, ms)
+    else:
+        tokens, ms = loop.run_steps(args.steps, timed=True)
     barrier()
     wall = time.time() - t_wall0
     clocks = sampler.stop()
@@ -459,7 +468,7 @@ def run_b200(args):
                    "accepted_tokens_per_step": round(acc_per_step, 4), "parallelism": f"target tp{world}, draft on rank 0",
                    "l2": "inputs larger than L2: each step streams the target's %.1f GB of weights" % (target.engine.runner.weight_bytes() / 1e9)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": extra,
-        "wall_s_timed_region": round(wall, 3), "device_errors": dev_err,
+        "wall_s_timed_region": round(wall, 3), "device_errors": dev_err, "profiled": bool(args.timeline),
         "phases": {"draft_ms_per_step": round(loop.draft_ms / args.steps, 4), "verify_ms_per_step": round(loop.verify_ms / args.steps, 4),
                    "note": "CUDA events around construct_grow_map() (draft tree, rank 0 only) and verify() (target forward over "
                            "all ranks + accept walk + KV compaction + 1-token draft forward) of the timed steps"},
@@ -474,6 +483,30 @@ def run_b200(args):
         out["cpu_baseline"] = cpu_reference(args.config, max_seconds=25.0, max_iters=3)
     print(json.dumps(out))
     finish(3 if (dev_err["peer_error"] or dev_err["attn_error"]) else 0)
+
+
+def write_timeline(prof, path, steps, ms):
+    """Markdown table: device time per kernel name over the timed steps, from the profiler's CUDA events."""
+    import collections
+    import re
+    tot = collections.defaultdict(lambda: [0, 0.0])
+    t_min, t_max, busy = None, None, 0.0
+    for ev in prof.events():
+        if ev.device_type is None or "cuda" not in str(ev.device_type).lower():
+            continue
+        dur = float(getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0) or 0.0)
+        if dur <= 0:
+            continue
+        name = re.sub(r"\(.*", "", re.sub(r"<.*", "", ev.name)).replace("void ", "")[:70]
+        tot[name][0] += 1
+        tot[name][1] += dur
+        busy += dur
+    with open(path, "w") as f:
+        f.write(f"In-graph device time per kernel over {steps} timed decode steps (torch.profiler / CUPTI, rank 0; "
+                f"CUDA-event time of the same steps {ms:.2f} ms; sum of kernel times {busy / 1e3:.2f} ms).\n\n")
+        f.write("| kernel | launches / step | us / step | share of kernel time | avg us |\n|---|---:|---:|---:|---:|\n")
+        for k, (c, d) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {c / steps:.1f} | {d / steps:.1f} | {100 * d / max(busy, 1e-9):.1f}% | {d / c:.2f} |\n")
 
 
 def run_sweep(args, dev):
@@ -809,6 +842,8 @@ def main():
     ap.add_argument("--no-micro", action="store_true", help="skip the per-kernel micro timings (for ncu launch lists)")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-on-this-GPU arm (N=1)")
     ap.add_argument("--no-tp-parity", action="store_true", help="skip the TP-vs-unsharded parity check (N>1)")
+    ap.add_argument("--timeline", default=None, help="write a per-kernel in-graph device-time table (markdown) of the timed "
+                                                     "steps to this file (torch.profiler; the run's value is then not a bench number)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -60,6 +60,8 @@ int sq_add_rmsnorm(sq_half* resid, const sq_half* delta, const sq_half* weight, 
                    float eps, void* stream);
 /* LlamaMLP_FI (Llama_modules.py:270-272): out = fp16(silu(gate)) * up, gate_up = [gate | up] rows of 2*inter. */
 int sq_silu_mul(const sq_half* gate_up, sq_half* out, int n, int inter, void* stream);
+/* interleaved = 1: gate_up rows are blocks of 32 = 16 gate | 16 up columns (the fused SwiGLU GEMM's weight row order). */
+int sq_silu_mul_ex(const sq_half* gate_up, sq_half* out, int n, int inter, int interleaved, void* stream);
 
 /* RoPE (transformers 4.36 apply_rotary_pos_emb, Llama_modules.py:117-118,213-214) applied in place to the
  * Q columns of the fused qkv rows, and K (rotated) + V appended to the cache at storage slots

@@ -26,6 +26,7 @@ _SIGNATURES = {
     "sq_rmsnorm": (i32, [vp, vp, vp, i32, i32, f32, vp]),
     "sq_add_rmsnorm": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
     "sq_silu_mul": (i32, [vp, vp, i32, i32, vp]),
+    "sq_silu_mul_ex": (i32, [vp, vp, i32, i32, i32, vp]),
     "sq_rope_kv_append": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp]),
     "sq_kv_gather": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp]),
     "sq_kv_gather_scratch_bytes": (i64, [i32, i32, i32, i32]),

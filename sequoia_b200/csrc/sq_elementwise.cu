@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(__half* __restrict__ resid
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restrict__ out, int n, int inter) {
+// interleaved = 0: gu row = [gate (inter) | up (inter)]; 1: blocks of 32 = 16 gate | 16 up (the row order of the fused
+// SwiGLU GEMM's weights, ops.interleave_gate_up)
+__global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restrict__ out, int n, int inter, int interleaved) {
   pdl_wait();
   pdl_trigger();
   const int64_t nvec = (int64_t)n * (inter / 8);
@@ -84,8 +86,14 @@ __global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restric
     const int64_t r = i / (inter / 8);
     const int c = (int)(i % (inter / 8));
     Pack8 g, u, o;
-    g.u = reinterpret_cast<const uint4*>(gu + r * 2 * inter)[c];
-    u.u = reinterpret_cast<const uint4*>(gu + r * 2 * inter + inter)[c];
+    if (interleaved) {
+      const int off = (c >> 1) * 32 + (c & 1) * 8;
+      g.u = *reinterpret_cast<const uint4*>(gu + r * 2 * inter + off);
+      u.u = *reinterpret_cast<const uint4*>(gu + r * 2 * inter + off + 16);
+    } else {
+      g.u = reinterpret_cast<const uint4*>(gu + r * 2 * inter)[c];
+      u.u = reinterpret_cast<const uint4*>(gu + r * 2 * inter + inter)[c];
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float x = h2f(g.h[j]);
@@ -181,12 +189,17 @@ extern "C" int sq_add_rmsnorm(sq_half* resid, const sq_half* delta, const sq_hal
 }
 
 extern "C" int sq_silu_mul(const sq_half* gate_up, sq_half* out, int n, int inter, void* stream) {
-  SQ_CHECK_ARG(inter % 8 == 0, "sq_silu_mul: inter %% 8 != 0");
+  return sq_silu_mul_ex(gate_up, out, n, inter, 0, stream);
+}
+
+extern "C" int sq_silu_mul_ex(const sq_half* gate_up, sq_half* out, int n, int inter, int interleaved, void* stream) {
+  SQ_CHECK_ARG(inter % 8 == 0 && (!interleaved || inter % 16 == 0), "sq_silu_mul: inter %% 8 != 0 (16 when interleaved)");
   if (n == 0) return SQ_OK;
   const int64_t nvec = (int64_t)n * (inter / 8);
   int blocks = (int)((nvec + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(silu_mul_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const __half*)gate_up, (__half*)out, n, inter);
+  launch_k(silu_mul_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const __half*)gate_up, (__half*)out, n, inter,
+           interleaved);
   SQ_CHECK_LAUNCH("sq_silu_mul");
   return SQ_OK;
 }

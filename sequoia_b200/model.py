@@ -262,25 +262,24 @@ class LlamaRunner:
                                       o=self._plan(self.attn_out, ly["wo"], self.proj),
                                       d=self._plan(self.act, ly["wd"], self.proj)))
         # (a fused-epilogue plan cannot split K, so a narrow shard -- TP-4/8 of a 7B -- would leave most SMs idle: those
-        # stay on cuBLASLt + sq_silu_mul; measured at TP-4: 4.15 ms / step with the plan vs 3.4 ms without)
+        # stay on cuBLASLt + sq_silu_mul).  The plans serve forwards of <= 128 rows; larger ones (prefill, the 768-row verify
+        # of config 4: compute-bound, not a weight stream) go to cuBLASLt on the SAME weight tensor, which is why gate_up is
+        # kept row-major in the interleaved order (16 gate rows | 16 up rows) rather than pre-tiled.
         gu_bn, gu_split, _ = ops.gemm_pick_tiles(2 * self.I, h, ops.GEMM_SWIGLU) if self.I % 16 == 0 and h % 64 == 0 else (0, 1, 1)
         gu_ctas = (-(-2 * self.I // gu_bn)) * gu_split if gu_bn else 0
+        self.gu_interleaved = False
         if mode in ("1", "auto") and stream_sized and gu_ctas >= 120:
+            self.gu_interleaved = True
             for ly in self.layers:
-                wil = ops.interleave_gate_up(ly["wgu"][:self.I], ly["wgu"][self.I:])
-                ly["wgu_bytes"] = ly["wgu"].numel() * 2
-                ly["wgu"] = None                          # the plan's tiled copy is the only resident one
-                ly["gu_plan"] = ops.GemmPlan(self.normed, wil, self.act, self.gemm_err, tiled=True, swiglu=True)
-                del wil
+                ly["wgu"] = ops.interleave_gate_up(ly["wgu"][:self.I], ly["wgu"][self.I:])
+                ly["gu_plan"] = ops.GemmPlan(self.normed, ly["wgu"], self.act, self.gemm_err, swiglu=True)
         if mode in ("1", "auto") and stream_sized and V % 32 == 0 and h % 64 == 0:
-            self.lm_plan = ops.GemmPlan(self.normed, self.lm_head, self.logits, self.gemm_err, tiled=True)
-            self.lm_head_bytes = self.lm_head.numel() * 2
-            self.lm_head = None
+            self.lm_plan = ops.GemmPlan(self.normed, self.lm_head, self.logits, self.gemm_err)
         # Small draft models: one persistent cooperative kernel per tree level instead of ~25 launches (csrc/sq_draft.cu);
         # tree-relative forwards of <= 64 rows take it, everything else (prefill, dense-mask API) the multi-kernel path.
         # SQ_DRAFT_FUSED=0 turns it off.
         self.draft_plan = None
-        if (os.environ.get("SQ_DRAFT_FUSED", "1") != "0" and tp == 1 and self.layers[0]["wgu"] is not None and
+        if (os.environ.get("SQ_DRAFT_FUSED", "1") != "0" and tp == 1 and not self.gu_interleaved and
                 ops.draft_supported(h, self.I, self.L, self.H, self.Hkv, D, V, max_length)):
             self.draft_plan = ops.DraftPlan(h, self.I, self.H, V, max_length, self.eps, self.embed, self.layers, self.norm,
                                             self.lm_head, self.cos, self.sin, self.k_cache, self.v_cache)
@@ -332,11 +331,11 @@ class LlamaRunner:
     def _gate_up_act(self, ly, n: int):
         """act[:n] = silu(normed[:n] @ Wg.T) * (normed[:n] @ Wu.T)   (Engine/Llama_modules.py:272)"""
         plan = ly.get("gu_plan")
-        if plan is not None:
+        if plan is not None and n <= 128:
             plan.run(n)
             return
         torch.mm(self.normed[:n], ly["wgu"].t(), out=self.gate_up[:n])
-        ops.silu_mul(self.gate_up, self.act, n)
+        ops.silu_mul(self.gate_up, self.act, n, interleaved=self.gu_interleaved)
 
     def _linear(self, l: int, key: str, x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, n: int):
         """out[:n] = x[:n] @ w.T"""
@@ -348,11 +347,10 @@ class LlamaRunner:
         torch.mm(x[:n], w.t(), out=out[:n])
 
     def weight_bytes(self) -> int:
-        b = 2 * (self.embed.numel() + self.norm.numel()) + (self.lm_head.numel() * 2 if self.lm_head is not None else self.lm_head_bytes)
+        b = self.embed.numel() + self.lm_head.numel() + self.norm.numel()
         for ly in self.layers:
-            b += 2 * sum(ly[k].numel() for k in ("wqkv", "wo", "wd", "ln1", "ln2"))
-            b += ly["wgu"].numel() * 2 if ly["wgu"] is not None else ly["wgu_bytes"]
-        return b
+            b += sum(ly[k].numel() for k in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2"))
+        return 2 * b
 
     @torch.no_grad()
     def forward(self, n: int, tokens: torch.Tensor, position_ids: torch.Tensor, storage_ids: torch.Tensor, *,
@@ -377,7 +375,7 @@ class LlamaRunner:
             self._prefetch_join()
             self._linear(l, "qkv", self.normed, ly["wqkv"], self.qkv, n)
             if self.pf_budget is not None:          # window A: RoPE + attention
-                self._prefetch(0, [(ly["wo"], 0)] + ([(ly["wgu"], 0)] if ly["wgu"] is not None else []))
+                self._prefetch(0, [(ly["wo"], 0), (ly["wgu"], 0)])
             ops.rope_kv_append(self.qkv, H, Hkv, D, self.cos, self.sin, position_ids, storage_ids, n,
                                self.k_cache[l], self.v_cache[l], M, state=state, n0=n0)
             ops.tree_attn(self.plan, l, n, state=state, n0=n0, kv_end=kv_end, prefix_len=prefix_len,
@@ -395,10 +393,9 @@ class LlamaRunner:
             self._linear(l, "o", self.attn_out, ly["wo"], self.proj, n)
             if self.pf_budget is not None:          # window B: residual + RMSNorm; continue gate_up where window A stopped
                 wo_b = ly["wo"].numel() * 2
-                if ly["wgu"] is not None:
-                    done = 0 if self.pf_budget[0] <= wo_b else \
-                        min(((self.pf_budget[0] - wo_b) // (ly["wgu"].shape[0] * 2)) // 64 * 64, ly["wgu"].shape[1])
-                    self._prefetch(1, [(ly["wgu"], done)])
+                done = 0 if self.pf_budget[0] <= wo_b else \
+                    min(((self.pf_budget[0] - wo_b) // (ly["wgu"].shape[0] * 2)) // 64 * 64, ly["wgu"].shape[1])
+                self._prefetch(1, [(ly["wgu"], done)])
             self.tp.all_reduce(self.proj[:n])
             ops.add_rmsnorm(self.hidden, self.proj, ly["ln2"], self.normed, n, self.eps)
             self._prefetch_join()
@@ -406,7 +403,7 @@ class LlamaRunner:
             self._prefetch_join()
             self._linear(l, "d", self.act, ly["wd"], self.proj, n)
             if self.pf_budget is not None:          # window D: residual + RMSNorm before the next layer's qkv / lm_head
-                nw = self.layers[l + 1]["wqkv"] if l + 1 < self.L else (None if skip_lm_head else self.lm_head)   # (None when tiled)
+                nw = self.layers[l + 1]["wqkv"] if l + 1 < self.L else (None if skip_lm_head else self.lm_head)
                 if nw is not None:
                     self._prefetch(3, [(nw, 0)])
             self.tp.all_reduce(self.proj[:n])
@@ -417,7 +414,7 @@ class LlamaRunner:
         self._prefetch_join()
         m = n - logits_from
         out = logits_out if logits_out is not None else self.logits[:m]
-        if self.lm_plan is not None and out.stride(-1) == 1 and out.stride(0) % 8 == 0 and out.data_ptr() % 16 == 0:
+        if self.lm_plan is not None and m <= 128 and out.stride(-1) == 1 and out.stride(0) % 8 == 0 and out.data_ptr() % 16 == 0:
             self.lm_plan.run(m, a_row0=logits_from, out=out)
         else:
             torch.mm(self.normed[logits_from:n], self.lm_head.t(), out=out)

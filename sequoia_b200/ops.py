@@ -38,9 +38,10 @@ def add_rmsnorm(resid, delta, weight, out, n, eps):
           "sq_add_rmsnorm")
 
 
-def silu_mul(gate_up, out, n):
+def silu_mul(gate_up, out, n, interleaved=False):
+    """out = silu(gate) * up; interleaved: gate_up columns in blocks of 32 = 16 gate | 16 up (interleave_gate_up order)."""
     lib = _lib.load()
-    check(lib.sq_silu_mul(ptr(gate_up), ptr(out), n, out.shape[-1], stream_ptr()), "sq_silu_mul")
+    check(lib.sq_silu_mul_ex(ptr(gate_up), ptr(out), n, out.shape[-1], 1 if interleaved else 0, stream_ptr()), "sq_silu_mul_ex")
 
 
 def rope_kv_append(qkv, H, Hkv, D, cos, sin, position_ids, storage_ids, n, k_layer, v_layer, M, state=None, n0=0):

@@ -769,6 +769,14 @@ def test_gemm_fused_swiglu_epilogue_bit_exact(I, K, n, tiled):
     nbad, _ = ulp_close(act[:n], ref, 2, atol=1e-3)
     assert nbad <= act[:n].numel() * 1e-3, f"{nbad} outputs beyond 2 ulp of the torch chain"
     assert (act[n:] == 7.0).all()
+    # the > 128-row route of the model: cuBLASLt on the SAME interleaved weight + sq_silu_mul in interleaved mode
+    wil = ops().interleave_gate_up(wg, wu)
+    gu2 = torch.mm(a[:n], wil.t())
+    act2 = torch.zeros(n, I, dtype=F16, device=DEV)
+    ops().silu_mul(gu2, act2, n, interleaved=True)
+    want2 = torch.zeros(n, I, dtype=F16, device=DEV)
+    ops().silu_mul(torch.cat([gu2.view(n, I // 16, 2, 16)[:, :, 0].reshape(n, I), gu2.view(n, I // 16, 2, 16)[:, :, 1].reshape(n, I)], 1).contiguous(), want2, n)
+    assert torch.equal(act2, want2), "interleaved silu_mul must equal the plain one on de-interleaved columns"
 
 
 # ------------------------------------------------------------------------------------------------ fused draft forward
@@ -827,8 +835,13 @@ def test_fused_draft_forward_matches_multi_kernel_path(hidden, inter, heads, lay
         worst = max(worst, rel)
         assert rel < 2e-3, f"level n0={n0} n={n}: fused draft logits differ by {rel:.3e}"
         sl = slice(P - 1 + n0, P - 1 + n0 + n)
-        for ca, cb in ((ref.k_cache, fused.k_cache), (ref.v_cache, fused.v_cache)):
-            nbad, _ = ulp_close(ca[:, :, :, sl], cb[:, :, :, sl], 2, atol=2e-4)
-            assert nbad <= ca[:, :, :, sl].numel() * 2e-3, f"level n0={n0}: {nbad} appended K/V values beyond 2 ulp"
+        # V rows are GEMM outputs: the two fp32 accumulation orders round to the same or the neighbouring fp16 value.  K rows
+        # went through RoPE (a*cos - b*sin of two such values, with cancellation): bounded relative to the row's magnitude.
+        va, vb = ref.v_cache[:, :, :, sl], fused.v_cache[:, :, :, sl]
+        nbad, _ = ulp_close(va, vb, 1, atol=1e-4)
+        assert nbad <= va.numel() * 2e-3, f"level n0={n0}: {nbad} appended V values beyond 1 ulp"
+        ka, kb = ref.k_cache[:, :, :, sl].float(), fused.k_cache[:, :, :, sl].float()
+        kerr = ((ka - kb).abs().amax(dim=-1) / ka.abs().amax(dim=-1).clamp(min=1e-3)).max().item()
+        assert kerr < 4e-3, f"level n0={n0}: appended K rows differ by {kerr:.3e} of the row's max"
     with open(os.path.join(os.path.dirname(G), "..", "gpurun_out", "logit_err.log"), "a") as f:
         f.write(f"fused draft forward (h={hidden} I={inter} L={layers}): max rel logit diff vs the multi-kernel path {worst:.3e}\n")
