@@ -269,6 +269,11 @@ int sq_draft_forward(sq_draft_plan* plan, int n, const int64_t* tokens, const in
                      const int32_t* state, int n0, int kv_end, const uint32_t* tree_bits, int tree_words, int tree_size,
                      sq_half* logits_out, int64_t ld_logits, void* stream);
 
+/* Only the attention phase of `layer`, as one launch on caller-owned buffers: q rows from `qkv` (n, 3*hidden), K/V from the
+ * plan's caches (rows already appended), output (n, hidden).  Small-shape alternative to sq_tree_attn for draft forwards. */
+int sq_draft_attention(sq_draft_plan* plan, int layer, int n, const sq_half* qkv, sq_half* attn_out, const int32_t* state,
+                       int n0, int kv_end, const uint32_t* tree_bits, int tree_words, int tree_size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

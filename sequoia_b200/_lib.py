@@ -67,6 +67,7 @@ _SIGNATURES = {
     "sq_draft_supported": (i32, [i32, i32, i32, i32, i32, i32, i32, i32]),
     "sq_draft_plan_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64]),
     "sq_draft_plan_destroy": (i32, [vp]),
+    "sq_draft_attention": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, i32, vp]),
     "sq_draft_forward": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, i64, vp]),
 }
 

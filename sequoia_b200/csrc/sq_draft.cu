@@ -86,36 +86,36 @@ struct DraftSmem {
 };
 
 // A_s <- rows of `src` (pitch ld_src halfs, `cols` columns starting at col0), rows >= n zero-filled; optional RMSNorm with
-// weight `nw` (nullptr = plain copy).  cols % 8 == 0.  Ends with a block barrier.
+// weight `nw` (nullptr = plain copy).  cols % 8 == 0.  All rows are fetched with cp.async first (one L2 round trip for the
+// whole tile instead of one per loop iteration), the norm then runs out of shared memory.  Waits for ALL outstanding
+// cp.async groups of the thread (weight sub-tiles issued before the call land under the same wait) and ends with a block
+// barrier.
 __device__ void load_A(const DraftSmem& sm, const __half* src, int64_t ld_src, int col0, int cols, int n, int n_pad,
-                       const __half* nw, float eps) {
+                       const __half* nw, float eps, bool chain) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cv = cols / 8;
-  if (nw == nullptr) {
-    for (int i = tid; i < n_pad * cv; i += DT) {
-      const int r = i / cv, c = i % cv;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (r < n) v = *reinterpret_cast<const uint4*>(src + r * ld_src + col0 + c * 8);
-      *reinterpret_cast<uint4*>(sm.A + r * sm.ld + c * 8) = v;
-    }
-  } else {
+  if (chain) pdl_wait();      // chained launches: the activations come from the previous kernel (weights were requested before)
+  for (int i = tid; i < n_pad * cv; i += DT) {
+    const int r = i / cv, c = i % cv;
+    __half* dst = sm.A + r * sm.ld + c * 8;
+    if (r < n) cp16(dst, src + r * ld_src + col0 + c * 8);
+    else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  }
+  cp_commit();
+  cp_wait<0>();
+  __syncthreads();
+  if (nw != nullptr) {
     // one warp per row: sum of squares, then x * inv -> fp16 -> * w -> fp16   (rmsnorm_kernel's arithmetic)
-    for (int r = warp; r < n_pad; r += DT / 32) {
-      if (r >= n) {
-        for (int c = lane; c < cv; c += 32) *reinterpret_cast<uint4*>(sm.A + r * sm.ld + c * 8) = make_uint4(0, 0, 0, 0);
-        continue;
-      }
+    for (int r = warp; r < n; r += DT / 32) {
       float ss = 0.f;
       for (int c = lane; c < cv; c += 32) {
         Pack8 v;
-        v.u = *reinterpret_cast<const uint4*>(src + r * ld_src + col0 + c * 8);
+        v.u = *reinterpret_cast<const uint4*>(sm.A + r * sm.ld + c * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float f = h2f(v.h[j]); ss += f * f; }
-        *reinterpret_cast<uint4*>(sm.A + r * sm.ld + c * 8) = v.u;      // raw copy first (re-read below from smem)
       }
       ss = warp_sum(ss);
       const float inv = rsqrtf(ss / (float)cols + eps);
-      __syncwarp();
       for (int c = lane; c < cv; c += 32) {
         Pack8 v, wv, o;
         v.u = *reinterpret_cast<const uint4*>(sm.A + r * sm.ld + c * 8);
@@ -125,8 +125,8 @@ __device__ void load_A(const DraftSmem& sm, const __half* src, int64_t ld_src, i
         *reinterpret_cast<uint4*>(sm.A + r * sm.ld + c * 8) = o.u;
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // async copy of `rows` weight rows (K columns from column k0) into W_s[buf]; `rowmap(i)` = global row of smem row i (< 0: zeros)
@@ -200,9 +200,16 @@ __device__ __forceinline__ void gemm_subtile(const DraftSmem& sm, int buf, int K
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a) {
+// Two ways to run the phases: coop = 1, ONE cooperative launch walks phases [phase_lo, phase_hi) with a grid barrier after
+// each; coop = 0, one launch per phase (phase_hi = phase_lo + 1), chained with programmatic dependent launch: weight
+// sub-tiles are requested before `griddepcontrol.wait`, activations after.  Phase ids: 0 = P0, 1 + 6l + {0..5} = A, B, C, D,
+// E, E2 of layer l, 1 + 6L = F.
+__global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a, int phase_lo, int phase_hi, int coop) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  cg::grid_group grid = cg::this_grid();
+  const bool chain = !coop;
+  if (chain) pdl_trigger();
+  auto run = [&](int ph) { return ph >= phase_lo && ph < phase_hi; };
+  auto phase_end = [&](int ph) { if (coop && run(ph) && ph + 1 < phase_hi) cg::this_grid().sync(); };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int h = a.h, n = a.n;
@@ -213,19 +220,23 @@ __global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a)
   sm.W[0] = sm.A + D_ROWS * sm.ld;
   sm.W[1] = sm.W[0] + 32 * sm.ld;
   sm.red = reinterpret_cast<float*>(sm.W[1] + 32 * sm.ld);       // 8 warps x 32 lanes x 8 floats = 8 KB
+  // (the prefix length only changes in the verify step, never between the launches of one draft phase)
   const int P = a.state[ST_P];
   const int base = P - 1;
   const int kv_len = base + a.kv_end;
   const int nblk = gridDim.x, bid = blockIdx.x;
 
   // ---- P0: hidden <- embedding rows -------------------------------------------------------------------------------------
-  for (int r = bid; r < n; r += nblk) {
-    const int64_t tok = a.tokens[base + a.n0 + r];
-    const uint4* src = reinterpret_cast<const uint4*>(a.embed + tok * (int64_t)h);
-    uint4* dst = reinterpret_cast<uint4*>(a.hidden + (int64_t)r * h);
-    for (int i = tid; i < h / 8; i += DT) dst[i] = src[i];
+  if (run(0)) {
+    if (chain) pdl_wait();
+    for (int r = bid; r < n; r += nblk) {
+      const int64_t tok = a.tokens[base + a.n0 + r];
+      const uint4* src = reinterpret_cast<const uint4*>(a.embed + tok * (int64_t)h);
+      uint4* dst = reinterpret_cast<uint4*>(a.hidden + (int64_t)r * h);
+      for (int i = tid; i < h / 8; i += DT) dst[i] = src[i];
+    }
   }
-  grid.sync();
+  phase_end(0);
 
   for (int l = 0; l < a.L; ++l) {
     const __half* wqkv = a.w[l][0];
@@ -237,13 +248,13 @@ __global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a)
 
     // ---- A: RMSNorm + q/k/v GEMM + RoPE + KV append.  Item = 16 dims of the first half of a head + their 16 partners in
     // the second half (rotate_half pairs dim d with d + 32): W_s rows [lo 0-7 | hi 0-7 | lo 8-15 | hi 8-15].
-    {
+    if (run(1 + 6 * l + 0)) {
       const int items = 3 * a.H * 2;
-      if (bid < items) load_A(sm, a.hidden, h, 0, h, n, n_pad, a.w[l][4], a.eps);
       for (int it = bid; it < items; it += nblk) {
         const int hd3 = it >> 1, q = it & 1;              // hd3: 0..H-1 q heads, H..2H-1 k heads, 2H..3H-1 v heads
         const int row0 = hd3 * HD + q * 16;
         load_W_async(sm, 0, wqkv, h, 0, h, 32, [&](int i) { return row0 + (i & 7) + ((i >> 4) << 3) + ((i >> 3) & 1) * 32; });
+        if (it == bid) load_A(sm, a.hidden, h, 0, h, n, n_pad, a.w[l][4], a.eps, chain);      // (waits for the weights too)
         cp_wait<0>();
         __syncthreads();
         const int kind = hd3 / a.H, head = hd3 % a.H;     // 0 q, 1 k, 2 v
@@ -285,11 +296,11 @@ __global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a)
         __syncthreads();
       }
     }
-    grid.sync();
+    phase_end(1 + 6 * l + 0);
 
     // ---- B: attention.  Item = (head, 16-row tile); the 8 warps take 32-key blocks round-robin (online softmax per warp),
     // partial (max, sum, O) combined through shared memory.
-    {
+    if (run(1 + 6 * l + 1)) {
       const int items = a.H * MT;
       const int ldk = HD + DPAD;                                       // 72 halfs
       __half* Ks = reinterpret_cast<__half*>(smem_raw);
@@ -299,6 +310,7 @@ __global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a)
       float* sO = reinterpret_cast<float*>(Qs + 16 * ldk);             // [8][16][64]
       float* sM = sO + 8 * 16 * 64;                                    // [8][16]
       float* sL = sM + 8 * 16;
+      if (chain) pdl_wait();
       for (int it = bid; it < items; it += nblk) {
         const int head = it / MT, mt = it % MT;
         const __half* kg = kc + (int64_t)head * a.M * HD;
@@ -453,15 +465,15 @@ __global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a)
         __syncthreads();
       }
     }
-    grid.sync();
+    phase_end(1 + 6 * l + 1);
 
     // ---- C: o_proj + residual add.  Item = 32 output columns.
-    {
+    if (run(1 + 6 * l + 2)) {
       const int items = h / 32;
-      if (bid < items) load_A(sm, a.attn, h, 0, h, n, n_pad, nullptr, 0.f);
       for (int it = bid; it < items; it += nblk) {
         const int c0 = it * 32;
         load_W_async(sm, 0, wo, h, 0, h, 32, [&](int i) { return c0 + i; });
+        if (it == bid) load_A(sm, a.attn, h, 0, h, n, n_pad, nullptr, 0.f, chain);
         cp_wait<0>();
         __syncthreads();
         gemm_subtile(sm, 0, h, MT, 2, [&](int mt, int np, float (&acc)[2][4]) {
@@ -481,12 +493,11 @@ __global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a)
         __syncthreads();
       }
     }
-    grid.sync();
+    phase_end(1 + 6 * l + 2);
 
     // ---- D: RMSNorm + gate/up + SiLU*up.  Item = 32 act columns = two 32-row sub-tiles [gate 0-7 | up 0-7 | gate 8-15 | up 8-15].
-    {
+    if (run(1 + 6 * l + 3)) {
       const int items = a.I / 32;
-      if (bid < items) load_A(sm, a.hidden, h, 0, h, n, n_pad, a.w[l][5], a.eps);
       for (int it = bid; it < items; it += nblk) {
         const int c0 = it * 32;
         auto rowmap = [&](int sub) {
@@ -494,6 +505,7 @@ __global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a)
         };
         load_W_async(sm, 0, wgu, h, 0, h, 32, rowmap(0));
         load_W_async(sm, 1, wgu, h, 0, h, 32, rowmap(1));
+        if (it == bid) load_A(sm, a.hidden, h, 0, h, n, n_pad, a.w[l][5], a.eps, chain);
         for (int sub = 0; sub < 2; ++sub) {
           if (sub == 0) cp_wait<1>(); else cp_wait<0>();
           __syncthreads();
@@ -516,16 +528,16 @@ __global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a)
         __syncthreads();
       }
     }
-    grid.sync();
+    phase_end(1 + 6 * l + 3);
 
     // ---- E: down_proj, split along K in chunks of h columns.  Item = (32 output columns, K chunk) -> fp32 partials.
-    {
+    if (run(1 + 6 * l + 4)) {
       const int ncol = h / 32;
       const int items = ncol * a.ks;
       for (int it = bid; it < items; it += nblk) {
         const int kq = it / ncol, c0 = (it % ncol) * 32;
         load_W_async(sm, 0, wd, a.I, kq * h, h, 32, [&](int i) { return c0 + i; });
-        load_A(sm, a.act, a.I, kq * h, h, n, n_pad, nullptr, 0.f);
+        load_A(sm, a.act, a.I, kq * h, h, n, n_pad, nullptr, 0.f, chain);
         cp_wait<0>();
         __syncthreads();
         gemm_subtile(sm, 0, h, MT, 2, [&](int mt, int np, float (&acc)[2][4]) {
@@ -542,9 +554,11 @@ __global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a)
         __syncthreads();
       }
     }
-    grid.sync();
+    phase_end(1 + 6 * l + 4);
 
     // ---- E2: hidden += fp16(sum of the K-chunk partials), in chunk order.
+    if (run(1 + 6 * l + 5)) {
+    if (chain) pdl_wait();
     for (int r = bid; r < n; r += nblk) {
       for (int c = tid * 2; c < h; c += DT * 2) {
         float s0 = 0.f, s1 = 0.f;
@@ -557,20 +571,21 @@ __global__ void __launch_bounds__(DT, 1) draft_forward_kernel(const DraftArgs a)
         *reinterpret_cast<uint32_t*>(p) = pack_h2(__low2float(old) + h2f(f2h(s0)), __high2float(old) + h2f(f2h(s1)));
       }
     }
-    grid.sync();
+    }
+    phase_end(1 + 6 * l + 5);
   }
 
   // ---- F: final RMSNorm + lm_head.  Item = `fcols` vocabulary columns, streamed in double-buffered 32-row sub-tiles.
-  {
+  if (run(1 + 6 * a.L)) {
     const int per = ((a.V + nblk - 1) / nblk + 31) & ~31;            // columns per CTA, multiple of 32
     const int c_begin = bid * per;
     if (c_begin < a.V) {
-      load_A(sm, a.hidden, h, 0, h, n, n_pad, a.fnorm, a.eps);
       const int nsub = (min(per, a.V - c_begin) + 31) / 32;
       auto rowmap = [&](int sub) {
         return [=](int i) { const int col = c_begin + sub * 32 + i; return col < a.V ? col : -1; };
       };
       load_W_async(sm, 0, a.lm_head, h, 0, h, 32, rowmap(0));
+      load_A(sm, a.hidden, h, 0, h, n, n_pad, a.fnorm, a.eps, chain);
       for (int sub = 0; sub < nsub; ++sub) {
         if (sub + 1 < nsub) { load_W_async(sm, (sub + 1) & 1, a.lm_head, h, 0, h, 32, rowmap(sub + 1)); cp_wait<1>(); }
         else cp_wait<0>();
@@ -601,6 +616,7 @@ using namespace sq;
 struct sq_draft_plan {
   DraftArgs base;
   int n_sm, smem;
+  int coop;          // 1: one cooperative launch per forward (grid barriers); 0: one PDL-chained launch per phase
   size_t ws_bytes;
 };
 
@@ -659,6 +675,10 @@ extern "C" int sq_draft_plan_create(sq_draft_plan** plan, int hidden, int inter,
   const size_t smem_gemm = (size_t)(D_ROWS + 64) * (hidden + DPAD) * 2 + 8 * 32 * 8 * 4;
   const size_t smem_attn = (size_t)(2 * ((max_length + 31) & ~31) + 16) * (HD + DPAD) * 2 + (8 * 16 * 64 + 2 * 8 * 16) * 4;
   p->smem = (int)(smem_gemm > smem_attn ? smem_gemm : smem_attn);
+  {
+    const char* e = getenv("SQ_DRAFT_FUSED");     // "coop": cooperative megakernel; anything else: chained phase kernels
+    p->coop = (e && e[0] == 'c' && e[1] == 'o') ? 1 : 0;
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || p->n_sm <= 0) p->n_sm = 148;
@@ -679,6 +699,30 @@ extern "C" int sq_draft_plan_destroy(sq_draft_plan* plan) {
 /* Forward `n` (<= 64) rows of tree nodes [n0, n0+n) in tree-relative addressing (base = state[P]-1): tokens / positions /
  * cache slots at index base+n0+r, keys [0, base+kv_end) visible under the packed tree mask.  Writes K/V of the rows to the
  * cache and their logits to logits_out (row pitch ld_logits). */
+/* Only the attention phase of layer `layer` (one PDL-chained launch), on caller-owned buffers: q rows in `qkv` (n, 3*hidden;
+ * q part read), output to `attn_out` (n, hidden).  K/V come from the plan's caches (the rows of this forward must already
+ * be appended).  A small-shape alternative to sq_tree_attn for the draft model's <= 64-row forwards. */
+extern "C" int sq_draft_attention(sq_draft_plan* plan, int layer, int n, const sq_half* qkv, sq_half* attn_out,
+                                  const int32_t* state, int n0, int kv_end, const uint32_t* tree_bits, int tree_words,
+                                  int tree_size, void* stream) {
+  SQ_CHECK_ARG(plan != nullptr && state != nullptr && qkv && attn_out, "sq_draft_attention: null argument");
+  SQ_CHECK_ARG(n >= 1 && n <= D_ROWS && layer >= 0 && layer < plan->base.L, "sq_draft_attention: n=%d / layer=%d out of range", n, layer);
+  SQ_CHECK_ARG(tree_words <= 32, "sq_draft_attention: tree_size > 1024 unsupported");
+  DraftArgs a = plan->base;
+  a.n = n; a.n0 = n0; a.kv_end = kv_end; a.state = state;
+  a.tokens = nullptr; a.position_ids = nullptr; a.storage_ids = nullptr;
+  a.qkv = (__half*)qkv; a.attn = (__half*)attn_out;
+  a.tree_bits = tree_bits; a.tree_words = tree_bits ? tree_words : 0; a.tree_size = tree_bits ? tree_size : 0;
+  a.logits = nullptr; a.ld_logits = 0;
+  const int ph = 1 + 6 * layer + 1;
+  int grid = a.H * ((n + 15) / 16);
+  if (grid > plan->n_sm) grid = plan->n_sm;
+  cudaError_t e = launch_k(draft_forward_kernel, dim3(grid), dim3(DT), (size_t)plan->smem, (cudaStream_t)stream, a, ph, ph + 1, 0);
+  if (e != cudaSuccess) { set_error("sq_draft_attention: launch failed: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
+  SQ_CHECK_LAUNCH("sq_draft_attention");
+  return SQ_OK;
+}
+
 extern "C" int sq_draft_forward(sq_draft_plan* plan, int n, const int64_t* tokens, const int64_t* position_ids,
                                 const int64_t* storage_ids, const int32_t* state, int n0, int kv_end,
                                 const uint32_t* tree_bits, int tree_words, int tree_size, sq_half* logits_out,
@@ -692,18 +736,42 @@ extern "C" int sq_draft_forward(sq_draft_plan* plan, int n, const int64_t* token
   a.tokens = tokens; a.position_ids = position_ids; a.storage_ids = storage_ids; a.state = state;
   a.tree_bits = tree_bits; a.tree_words = tree_bits ? tree_words : 0; a.tree_size = tree_bits ? tree_size : 0;
   a.logits = (__half*)logits_out; a.ld_logits = ld_logits;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(plan->n_sm);
-  cfg.blockDim = dim3(DT);
-  cfg.dynamicSmemBytes = plan->smem;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative;
-  at[0].val.cooperative = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, draft_forward_kernel, a);
-  if (e != cudaSuccess) { set_error("sq_draft_forward: launch failed: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
+  const int n_phases = 2 + 6 * a.L;
+  if (plan->coop) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(plan->n_sm);
+    cfg.blockDim = dim3(DT);
+    cfg.dynamicSmemBytes = plan->smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, draft_forward_kernel, a, 0, n_phases, 1);
+    if (e != cudaSuccess) { set_error("sq_draft_forward: launch failed: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
+  } else {
+    const int MT = (n + 15) / 16;
+    for (int ph = 0; ph < n_phases; ++ph) {
+      int grid;
+      if (ph == 0) grid = n;
+      else if (ph == n_phases - 1) grid = plan->n_sm;
+      else {
+        switch ((ph - 1) % 6) {
+          case 0: grid = 6 * a.H; break;
+          case 1: grid = a.H * MT; break;
+          case 2: grid = a.h / 32; break;
+          case 3: grid = a.I / 32; break;
+          case 4: grid = (a.h / 32) * a.ks; break;
+          default: grid = n; break;
+        }
+      }
+      if (grid > plan->n_sm) grid = plan->n_sm;
+      cudaError_t e = launch_k(draft_forward_kernel, dim3(grid), dim3(DT), (size_t)plan->smem, (cudaStream_t)stream, a, ph, ph + 1, 0);
+      if (e != cudaSuccess) { set_error("sq_draft_forward: launch failed: %s", cudaGetErrorString(e)); return SQ_ERR_CUDA; }
+      if (ph + 1 < n_phases) sq::count_launch(1);
+    }
+  }
   SQ_CHECK_LAUNCH("sq_draft_forward");
   return SQ_OK;
 }

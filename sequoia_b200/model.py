@@ -275,11 +275,14 @@ class LlamaRunner:
                 ly["gu_plan"] = ops.GemmPlan(self.normed, ly["wgu"], self.act, self.gemm_err, swiglu=True)
         if mode in ("1", "auto") and stream_sized and V % 32 == 0 and h % 64 == 0:
             self.lm_plan = ops.GemmPlan(self.normed, self.lm_head, self.logits, self.gemm_err)
-        # Small draft models: one persistent cooperative kernel per tree level instead of ~25 launches (csrc/sq_draft.cu);
-        # tree-relative forwards of <= 64 rows take it, everything else (prefill, dense-mask API) the multi-kernel path.
-        # SQ_DRAFT_FUSED=0 turns it off.
+        # Small draft models (csrc/sq_draft.cu).  SQ_DRAFT_FUSED = "chain" | "coop": the whole forward of a tree level as
+        # PDL-chained phase kernels / ONE persistent cooperative kernel (measured SLOWER than the multi-kernel path on a
+        # B200 -- 103 / 121 us vs 84 us per level, DESIGN.md section 7 -- so it is opt-in).  Default: only its attention
+        # phase replaces sq_tree_attn for the draft's tree-relative forwards of <= 64 rows (SQ_DRAFT_ATTN=0 turns that off).
         self.draft_plan = None
-        if (os.environ.get("SQ_DRAFT_FUSED", "1") != "0" and tp == 1 and not self.gu_interleaved and
+        self.draft_fused = os.environ.get("SQ_DRAFT_FUSED", "0") not in ("0", "")
+        self.draft_attn = os.environ.get("SQ_DRAFT_ATTN", "1") != "0"
+        if ((self.draft_fused or self.draft_attn) and tp == 1 and not self.gu_interleaved and
                 ops.draft_supported(h, self.I, self.L, self.H, self.Hkv, D, V, max_length)):
             self.draft_plan = ops.DraftPlan(h, self.I, self.H, V, max_length, self.eps, self.embed, self.layers, self.norm,
                                             self.lm_head, self.cos, self.sin, self.k_cache, self.v_cache)
@@ -362,8 +365,9 @@ class LlamaRunner:
         Logits of rows [logits_from, n) are written to `logits_out` (default: the internal buffer) and returned."""
         assert 0 < n <= self.n_max
         H, Hkv, D, M = self.H, self.Hkv, self.D, self.M
-        if (self.draft_plan is not None and state is not None and n <= ops.DraftPlan.MAX_ROWS and dense_mask is None
-                and logits_from == 0 and not skip_lm_head and self.attn_impl == 0):
+        small = (self.draft_plan is not None and state is not None and n <= ops.DraftPlan.MAX_ROWS and dense_mask is None
+                 and self.attn_impl == 0)
+        if small and self.draft_fused and logits_from == 0 and not skip_lm_head:
             out = logits_out if logits_out is not None else self.logits[:n]
             self.draft_plan.forward(n, tokens, position_ids, storage_ids, state, n0, kv_end, tree_bits, tree_words,
                                     tree_size, out)
@@ -378,9 +382,12 @@ class LlamaRunner:
                 self._prefetch(0, [(ly["wo"], 0), (ly["wgu"], 0)])
             ops.rope_kv_append(self.qkv, H, Hkv, D, self.cos, self.sin, position_ids, storage_ids, n,
                                self.k_cache[l], self.v_cache[l], M, state=state, n0=n0)
-            ops.tree_attn(self.plan, l, n, state=state, n0=n0, kv_end=kv_end, prefix_len=prefix_len,
-                          dense_mask=dense_mask, mask_ld=mask_ld, tree_bits=tree_bits, tree_words=tree_words,
-                          tree_size=tree_size, impl=self.attn_impl)
+            if small and self.draft_attn:
+                self.draft_plan.attention(l, n, self.qkv, self.attn_out, state, n0, kv_end, tree_bits, tree_words, tree_size)
+            else:
+                ops.tree_attn(self.plan, l, n, state=state, n0=n0, kv_end=kv_end, prefix_len=prefix_len,
+                              dense_mask=dense_mask, mask_ld=mask_ld, tree_bits=tree_bits, tree_words=tree_words,
+                              tree_size=tree_size, impl=self.attn_impl)
             nxt = self.layers[l + 1]["ln1"] if l + 1 < self.L else self.norm
             if self.peer is not None:
                 torch.mm(self.attn_out[:n], ly["wo"].t(), out=self.peer.buf[0][:n])

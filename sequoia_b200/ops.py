@@ -298,6 +298,10 @@ class DraftPlan:
                                            kv_end, ptr(tree_bits), tree_words, tree_size, ptr(logits_out),
                                            logits_out.stride(0), stream_ptr()), "sq_draft_forward")
 
+    def attention(self, layer, n, qkv, attn_out, state, n0, kv_end, tree_bits, tree_words, tree_size):
+        check(_lib.load().sq_draft_attention(self.handle, layer, n, ptr(qkv), ptr(attn_out), ptr(state), n0, kv_end,
+                                             ptr(tree_bits), tree_words, tree_size, stream_ptr()), "sq_draft_attention")
+
     def __del__(self):
         try:
             if self.handle:
