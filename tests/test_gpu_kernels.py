@@ -794,13 +794,19 @@ def test_fused_draft_forward_matches_multi_kernel_path(hidden, inter, heads, lay
     w = O.init_llama_weights(cfg, 4242)
     spec = {"config": cfg, "state_dict": w}
     os.environ["SQ_DRAFT_FUSED"] = "0"
+    os.environ["SQ_DRAFT_ATTN"] = "0"
     try:
-        ref = LlamaRunner(spec, M, device=DEV)
-        os.environ["SQ_DRAFT_FUSED"] = mode      # "chain": one PDL-chained launch per phase; "coop": one cooperative launch
+        ref = LlamaRunner(spec, M, device=DEV)   # pure multi-kernel path incl. the tcgen05 attention kernel
+        # "attn" (the default): only the small-shape attention phase replaces sq_tree_attn; "chain": the whole forward as
+        # PDL-chained phase launches; "coop": one cooperative launch
+        os.environ["SQ_DRAFT_ATTN"] = "1"
+        os.environ["SQ_DRAFT_FUSED"] = "0" if mode == "attn" else mode
         fused = LlamaRunner(spec, M, device=DEV)
     finally:
         os.environ.pop("SQ_DRAFT_FUSED", None)
-    assert ref.draft_plan is None and fused.draft_plan is not None, "the fused draft kernel must engage for this shape"
+        os.environ.pop("SQ_DRAFT_ATTN", None)
+    assert ref.draft_plan is None and fused.draft_plan is not None, "the draft kernels must engage for this shape"
+    assert fused.draft_fused == (mode != "attn")
     gm = cases.load_growmap("A100_growmaps/68m_7b/growmaps/A100-CNN-68m-7b-stochastic.pt")
     S = gm["size"]
     P = 96
