@@ -250,6 +250,14 @@ int sq_tp_allreduce2_add_rmsnorm(sq_half* resid, const void* const* host_proj_pt
                                  void* const* host_flag_ptrs, void* const* host_rowflag_ptrs, uint32_t* epoch, int rank,
                                  int N, const sq_half* weight, sq_half* out, int n, int hidden, float eps, void* stream);
 
+/* One-shot PUSH variant for small payloads: every rank stores its partial row (proj_local, (n, hidden)) into receive slot
+ * [rank][row] of every peer (host_recv_ptrs[r] = (N, rows_max, hidden) fp16 area on rank r for this buffer parity), one system
+ * fence, per-(source, row) epoch flags (host_pflag_ptrs[r] = (N, rows_max) uint32 on rank r), then reduces from LOCAL memory in
+ * rank order + residual + RMSNorm.  One NVLink one-way trip instead of flag + fetch. */
+int sq_tp_allreduce3_add_rmsnorm(sq_half* resid, const sq_half* proj_local, void* const* host_recv_ptrs,
+                                 void* const* host_pflag_ptrs, uint32_t* epoch, int rank, int N, int rows_max,
+                                 const sq_half* weight, sq_half* out, int n, int hidden, float eps, void* stream);
+
 /* ---- fused draft forward (csrc/sq_draft.cu): one persistent cooperative kernel per tree level for small draft models
  * (Engine/Engine.py:158-164 replays a ~25-kernel graph per level; Tree/SpecTree.py:245-259).  Supported: head_dim 64,
  * n_heads * 64 == hidden, no GQA, intermediate %% hidden == 0, <= 16 layers, max_length <= 512 (see sq_draft_supported).

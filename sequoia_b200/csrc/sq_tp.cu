@@ -273,6 +273,115 @@ __global__ void __launch_bounds__(256) tp_allreduce2_add_rmsnorm_kernel(Tp2Args 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// One-shot PUSH variant for small payloads (the 128-row verify of a 7B: 1 MB): the pull kernels above need the partial to
+// be announced (flag, one NVLink trip) and then fetched (a round trip); here every rank WRITES its partial row into a
+// receive slot on every peer, fences once, raises a per-(source, row) flag, and then only reads LOCAL memory.  Measured
+// in-graph at TP-8 the two-shot kernel took 21.7 us per reduction (39 % of the step, profiles/r02_timeline_c2_tp8.md).
+// Receive slots alternate with the partial buffers (A / B), so a sender can be at most one reduction ahead of a reader.
+struct Tp3Args {
+  const __half* proj;        // this rank's partial GEMM output (local)
+  __half* recv[8];           // recv[r] = receive area on rank r: (N sources, rows_max, hidden) fp16 for THIS buffer parity
+  uint32_t* pflags[8];       // pflags[r] = per-(source, row) epoch words on rank r: (N, rows_max)
+  uint32_t* epoch;
+  int rank, N, rows_max;
+};
+
+template <int MAXV>
+__global__ void __launch_bounds__(256) tp_allreduce3_add_rmsnorm_kernel(Tp3Args t, __half* __restrict__ resid,
+                                                                        const __half* __restrict__ w,
+                                                                        __half* __restrict__ out, int hidden, float eps) {
+  __shared__ float red[8];
+  const int r = blockIdx.x, tid = threadIdx.x, N = t.N, rank = t.rank;
+  pdl_wait();                                                // the row-parallel GEMM's partial is complete and visible
+  pdl_trigger();
+  const uint32_t e = t.epoch[0] + 1;
+  const int nvec = hidden / 8;
+  Pack8 mine[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    mine[i].u = make_uint4(0, 0, 0, 0);
+    if (c < nvec) mine[i].u = reinterpret_cast<const uint4*>(t.proj + (int64_t)r * hidden)[c];
+  }
+  // phase 1: push my row into slot [rank][r] of every peer
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    if (c < nvec) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s)
+        if (s < N && s != rank)
+          st_relaxed_sys_v4(reinterpret_cast<uint4*>(t.recv[s] + ((int64_t)rank * t.rows_max + r) * hidden) + c, mine[i].u);
+    }
+  }
+  __syncthreads();                                            // every thread's remote stores are issued ...
+  if (tid < N && tid != rank) {
+    __threadfence_system();                                   // ... and ordered before the flag (cumulative release)
+    st_release_sys(t.pflags[tid] + rank * t.rows_max + r, e);
+    // phase 2: wait for the same row from that peer
+    const uint32_t* f = t.pflags[rank] + tid * t.rows_max + r;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(f) - e) < 0) {
+      if (clock64() - t0 > 4000000000LL) { atomicExch(t.epoch + 2, 3u); break; }
+    }
+  }
+  __syncthreads();
+  Pack8 v[MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    if (c < nvec) {
+      Pack8 part[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        part[s].u = make_uint4(0, 0, 0, 0);
+        if (s < N) part[s].u = (s == rank) ? mine[i].u
+                                           : ld_relaxed_sys_v4(reinterpret_cast<const uint4*>(t.recv[rank] + ((int64_t)s * t.rows_max + r) * hidden) + c);
+      }
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int s = 0; s < 8; ++s)                             // fixed rank order => every rank computes the same bits
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += h2f(part[s].h[j]);
+      Pack8 a;
+      a.u = reinterpret_cast<const uint4*>(resid + (int64_t)r * hidden)[c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __half x = f2h(acc[j]);
+        v[i].h[j] = f2h(h2f(a.h[j]) + h2f(x));
+        const float f = h2f(v[i].h[j]);
+        ss += f * f;
+      }
+      reinterpret_cast<uint4*>(resid + (int64_t)r * hidden)[c] = v[i].u;
+    }
+  }
+  ss = block_sum<8>(ss, red);
+  const float inv = rsqrtf(ss / (float)hidden + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    if (c < nvec) {
+      Pack8 wv, o;
+      wv.u = reinterpret_cast<const uint4*>(w)[c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.h[j] = f2h(h2f(wv.h[j]) * h2f(f2h(h2f(v[i].h[j]) * inv)));
+      reinterpret_cast<uint4*>(out + (int64_t)r * hidden)[c] = o.u;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t ticket = atomicAdd(t.epoch + 1, 1u);
+    if (ticket == gridDim.x - 1) {
+      t.epoch[1] = 0u;
+      __threadfence();
+      t.epoch[0] = e;
+    }
+  }
+}
+
 }  // namespace sq
 
 using namespace sq;
@@ -361,5 +470,30 @@ extern "C" int sq_tp_allreduce2_add_rmsnorm(sq_half* resid, const void* const* h
   else if (nvec <= 1024) launch_k(tp_allreduce2_add_rmsnorm_kernel<4>, dim3(n), dim3(256), 0, st, t, r, w, o, n, hidden, eps);
   else launch_k(tp_allreduce2_add_rmsnorm_kernel<8>, dim3(n), dim3(256), 0, st, t, r, w, o, n, hidden, eps);
   SQ_CHECK_LAUNCH("sq_tp_allreduce2_add_rmsnorm");
+  return SQ_OK;
+}
+
+extern "C" int sq_tp_allreduce3_add_rmsnorm(sq_half* resid, const sq_half* proj_local, void* const* host_recv_ptrs,
+                                            void* const* host_pflag_ptrs, uint32_t* epoch, int rank, int N, int rows_max,
+                                            const sq_half* weight, sq_half* out, int n, int hidden, float eps, void* stream) {
+  SQ_CHECK_ARG(N >= 2 && N <= 8 && rank >= 0 && rank < N, "sq_tp_allreduce3_add_rmsnorm: bad rank/N %d/%d", rank, N);
+  SQ_CHECK_ARG(hidden % 8 == 0 && hidden <= 256 * 8 * 8, "sq_tp_allreduce3_add_rmsnorm: hidden=%d unsupported", hidden);
+  SQ_CHECK_ARG(n <= rows_max, "sq_tp_allreduce3_add_rmsnorm: n=%d exceeds the receive area (%d rows)", n, rows_max);
+  if (n == 0) return SQ_OK;
+  Tp3Args t;
+  t.proj = (const __half*)proj_local;
+  for (int i = 0; i < 8; ++i) {
+    t.recv[i] = i < N ? (__half*)host_recv_ptrs[i] : nullptr;
+    t.pflags[i] = i < N ? (uint32_t*)host_pflag_ptrs[i] : nullptr;
+  }
+  t.epoch = epoch; t.rank = rank; t.N = N; t.rows_max = rows_max;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nvec = hidden / 8;
+  __half* r = (__half*)resid; const __half* w = (const __half*)weight; __half* o = (__half*)out;
+  if (nvec <= 256) launch_k(tp_allreduce3_add_rmsnorm_kernel<1>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
+  else if (nvec <= 512) launch_k(tp_allreduce3_add_rmsnorm_kernel<2>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
+  else if (nvec <= 1024) launch_k(tp_allreduce3_add_rmsnorm_kernel<4>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
+  else launch_k(tp_allreduce3_add_rmsnorm_kernel<8>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
+  SQ_CHECK_LAUNCH("sq_tp_allreduce3_add_rmsnorm");
   return SQ_OK;
 }

@@ -32,12 +32,19 @@ class PeerBuffers:
         self.n_max, self.hidden = n_max, hidden
         part = n_max * hidden * 2
         rowflag_bytes = ((n_max * 4 + 1023) // 1024) * 1024
-        total = 4 * part + 2 * self.FLAG_BYTES + 2 * rowflag_bytes
+        # one-shot PUSH (small payloads): receive slots for <= push_rows rows from each source, per buffer parity
+        self.push_rows = min(n_max, 256)
+        recv_bytes = self.N * self.push_rows * hidden * 2
+        pflag_bytes = ((self.N * self.push_rows * 4 + 1023) // 1024) * 1024
+        total = 4 * part + 2 * self.FLAG_BYTES + 2 * rowflag_bytes + 2 * recv_bytes + pflag_bytes
         # one-shot (every rank pulls all partials) below 4 ranks, two-shot (reduce-scatter + all-gather in one kernel)
         # from 4 ranks up; SQ_TP_SHOT=1|2 overrides
         import os
         shot = os.environ.get("SQ_TP_SHOT", "")
         self.two_shot = (shot == "2") or (shot != "1" and self.N >= 4)
+        # shot 3 = one-shot push: default whenever every peer's copy of the payload stays small (<= 8 MB pushed per rank)
+        self.push_ok = shot in ("", "3")
+        self.push_bytes_max = 8 << 20
         base = C.c_void_p()
         check(lib.sq_tp_alloc(C.byref(base), total), "sq_tp_alloc")
         self.base = base.value
@@ -63,6 +70,9 @@ class PeerBuffers:
         self.epoch_ptr = self.base + 4 * part + self.FLAG_BYTES
         rf0 = 4 * part + 2 * self.FLAG_BYTES
         self.rowflag_ptrs = [arr(*[(b + rf0 + w * rowflag_bytes) for b in self.bases] + [None] * (8 - self.N)) for w in range(2)]
+        rv0 = rf0 + 2 * rowflag_bytes
+        self.recv_ptrs = [arr(*[(b + rv0 + w * recv_bytes) for b in self.bases] + [None] * (8 - self.N)) for w in range(2)]
+        self.pflag_ptrs = arr(*[(b + rv0 + 2 * recv_bytes) for b in self.bases] + [None] * (8 - self.N))
         self.buf = [torch.as_tensor(_CudaArray(self.base + w * part, (n_max, hidden)), device=self.device) for w in range(2)]
         assert self.buf[0].data_ptr() == self.base and self.buf[0].dtype == torch.float16
         dist.barrier(group=group)                      # every rank has mapped every peer before the first kernel runs
@@ -70,6 +80,12 @@ class PeerBuffers:
     def allreduce_add_rmsnorm(self, which: int, resid: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, n: int,
                               eps: float):
         """resid += sum over ranks of partial buffer `which`; out = rmsnorm(resid) * weight  (one kernel per rank)."""
+        if self.push_ok and n <= self.push_rows and (self.N - 1) * n * self.hidden * 2 <= self.push_bytes_max:
+            check(_lib.load().sq_tp_allreduce3_add_rmsnorm(ptr(resid), self.buf[which].data_ptr(), self.recv_ptrs[which],
+                                                           self.pflag_ptrs, self.epoch_ptr, self.rank, self.N, self.push_rows,
+                                                           ptr(weight), ptr(out), n, self.hidden, eps, stream_ptr()),
+                  "sq_tp_allreduce3_add_rmsnorm")
+            return
         if self.two_shot:
             check(_lib.load().sq_tp_allreduce2_add_rmsnorm(ptr(resid), self.proj_ptrs[which], self.red_ptrs[which],
                                                            self.flag_ptrs, self.rowflag_ptrs[which], self.epoch_ptr,
