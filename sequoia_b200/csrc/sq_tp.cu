@@ -277,8 +277,11 @@ __global__ void __launch_bounds__(256) tp_allreduce2_add_rmsnorm_kernel(Tp2Args 
 // ------------------------------------------------------------------------------------------------------------------
 // One-shot PUSH variant for small payloads (the 128-row verify of a 7B: 1 MB): the pull kernels above need the partial to
 // be announced (flag, one NVLink trip) and then fetched (a round trip); here every rank WRITES its partial row into a
-// receive slot on every peer, fences once, raises a per-(source, row) flag, and then only reads LOCAL memory.  Measured
-// in-graph at TP-8 the two-shot kernel took 21.7 us per reduction (39 % of the step, profiles/r02_timeline_c2_tp8.md).
+// receive slot on every peer, fences once, raises a per-(source, row) flag, and then only reads LOCAL memory.  (In-graph at
+// TP-8 the two-shot kernel takes 21.7 us per reduction, 39 % of the step: profiles/r02_timeline_c2_tp8.md.)  Parity-green at
+// TP-2 but NOT faster (18.5 vs 12.7 us per reduction): `__threadfence_system` between the remote stores and the flag waits
+// for the stores to be acknowledged, i.e. the same round trip.  Opt-in (SQ_TP_SHOT=3); an LL-style protocol (flag packed with
+// the data, no fence) would be the next step.
 // Receive slots alternate with the partial buffers (A / B), so a sender can be at most one reduction ahead of a reader.
 struct Tp3Args {
   const __half* proj;        // this rank's partial GEMM output (local)

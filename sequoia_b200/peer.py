@@ -42,8 +42,10 @@ class PeerBuffers:
         import os
         shot = os.environ.get("SQ_TP_SHOT", "")
         self.two_shot = (shot == "2") or (shot != "1" and self.N >= 4)
-        # shot 3 = one-shot push: default whenever every peer's copy of the payload stays small (<= 8 MB pushed per rank)
-        self.push_ok = shot in ("", "3")
+        # shot 3 = one-shot PUSH for small payloads (<= 8 MB pushed per rank).  Opt-in: measured at TP-2 on c2 it is slower
+        # than the pull kernel (4.02 vs 3.68 ms / step; 18.5 vs 12.7 us per reduction) -- the system fence between the remote
+        # stores and the flag costs the round trip that the pull spends on its loads.
+        self.push_ok = shot == "3"
         self.push_bytes_max = 8 << 20
         base = C.c_void_p()
         check(lib.sq_tp_alloc(C.byref(base), total), "sq_tp_alloc")
