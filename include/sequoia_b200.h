@@ -258,6 +258,14 @@ int sq_tp_allreduce3_add_rmsnorm(sq_half* resid, const sq_half* proj_local, void
                                  void* const* host_pflag_ptrs, uint32_t* epoch, int rank, int N, int rows_max,
                                  const sq_half* weight, sq_half* out, int n, int hidden, float eps, void* stream);
 
+/* LL two-shot for small payloads: every 8-byte word crossing NVLink carries two halfs + the reduction's epoch (one atomic
+ * store), readers poll the words they need -- no flags, no fences, two one-way trips.  host_ll1_ptrs[r]: gather area on rank r,
+ * (N, own_max, hidden/4) 16-byte pairs; host_ll2_ptrs[r]: reduced-row area on rank r, (rows_max, hidden/4) pairs; both for this
+ * buffer parity, zero-initialised.  Row r is owned by rank r %% N. */
+int sq_tp_allreduce_ll_add_rmsnorm(sq_half* resid, const sq_half* proj_local, void* const* host_ll1_ptrs,
+                                   void* const* host_ll2_ptrs, uint32_t* epoch, int rank, int N, int rows_max, int own_max,
+                                   const sq_half* weight, sq_half* out, int n, int hidden, float eps, void* stream);
+
 /* ---- fused draft forward (csrc/sq_draft.cu): one persistent cooperative kernel per tree level for small draft models
  * (Engine/Engine.py:158-164 replays a ~25-kernel graph per level; Tree/SpecTree.py:245-259).  Supported: head_dim 64,
  * n_heads * 64 == hidden, no GQA, intermediate %% hidden == 0, <= 16 layers, max_length <= 512 (see sq_draft_supported).

@@ -385,6 +385,142 @@ __global__ void __launch_bounds__(256) tp_allreduce3_add_rmsnorm_kernel(Tp3Args 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// LL ("low latency") two-shot for small payloads: no flags and no fences -- every 8-byte word that crosses NVLink carries
+// 4 bytes of data (two halfs) and the 4-byte epoch of this reduction, written with ONE store (8-byte stores are atomic), and
+// the reader simply polls the words it needs until their epoch matches (the scheme of NCCL's LL protocol).  Row r is owned
+// by rank r % N:   (1) every non-owner pushes its partial row to the owner's slot [src][r / N];   (2) the owner polls the
+// N-1 slots, sums in rank order in fp32, rounds to fp16 and pushes the reduced row to every peer's slot [r];   (3) the others
+// poll that slot.  Two one-way NVLink trips, no round trip, 2x the bytes (fine for the 128-row verify of a 7B: 3.6 MB per rank
+// at TP-8).  Slots alternate with the partial buffers (A / B); a sender can be at most one reduction ahead of any reader
+// because completing a reduction needs a word from every owner.
+struct TpLLArgs {
+  const __half* proj;        // this rank's partial GEMM output (local)
+  uint4* ll1[8];             // ll1[r] = gather area on rank r: (N sources, own_max rows, hidden/4 pairs) for this parity
+  uint4* ll2[8];             // ll2[r] = reduced-row area on rank r: (rows_max, hidden/4 pairs)
+  uint32_t* epoch;
+  int rank, N, rows_max, own_max;
+};
+
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ll_wait(const uint4* p, uint32_t e, uint32_t* err) {
+  const long long t0 = clock64();
+  uint4 v = ld_volatile_v4(p);
+  while (v.y != e || v.w != e) {
+    if (clock64() - t0 > 4000000000LL) { atomicExch(err, 4u); break; }      // ~2 s: never hang the box
+    v = ld_volatile_v4(p);
+  }
+  return make_uint2(v.x, v.z);
+}
+
+template <int MAXP>   // 16-byte pairs (4 halfs of payload) per thread: hidden <= 256 * 4 * MAXP
+__global__ void __launch_bounds__(256) tp_allreduce_ll_add_rmsnorm_kernel(TpLLArgs t, __half* __restrict__ resid,
+                                                                          const __half* __restrict__ w,
+                                                                          __half* __restrict__ out, int hidden, float eps) {
+  __shared__ float red[8];
+  const int r = blockIdx.x, tid = threadIdx.x, N = t.N, rank = t.rank;
+  pdl_wait();                                                // the row-parallel GEMM's partial is complete and visible
+  pdl_trigger();
+  const uint32_t e = t.epoch[0] + 1;
+  const int npair = hidden / 4;
+  const int owner = r % N, lrow = r / N;
+  uint2 mine[MAXP], redv[MAXP];
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    const int p = tid + i * 256;
+    mine[i] = make_uint2(0u, 0u);
+    if (p < npair) mine[i] = reinterpret_cast<const uint2*>(t.proj + (int64_t)r * hidden)[p];
+  }
+  if (owner != rank) {
+    // (1) push my partial row to the owner
+    uint4* dst = t.ll1[owner] + ((int64_t)rank * t.own_max + lrow) * npair;
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+      const int p = tid + i * 256;
+      if (p < npair) st_relaxed_sys_v4(dst + p, make_uint4(mine[i].x, e, mine[i].y, e));
+    }
+    // (3) poll the reduced row
+    const uint4* src = t.ll2[rank] + (int64_t)r * npair;
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+      const int p = tid + i * 256;
+      redv[i] = make_uint2(0u, 0u);
+      if (p < npair) redv[i] = ll_wait(src + p, e, t.epoch + 2);
+    }
+  } else {
+    // (2) owner: gather, reduce in rank order, scatter
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+      const int p = tid + i * 256;
+      redv[i] = make_uint2(0u, 0u);
+      if (p < npair) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < N; ++s) {
+          const uint2 v = (s == rank) ? mine[i] : ll_wait(t.ll1[rank] + ((int64_t)s * t.own_max + lrow) * npair + p, e, t.epoch + 2);
+          const __half2 a = *reinterpret_cast<const __half2*>(&v.x), b = *reinterpret_cast<const __half2*>(&v.y);
+          acc[0] += __low2float(a); acc[1] += __high2float(a); acc[2] += __low2float(b); acc[3] += __high2float(b);
+        }
+        const __half2 lo = __floats2half2_rn(acc[0], acc[1]), hi = __floats2half2_rn(acc[2], acc[3]);
+        redv[i].x = *reinterpret_cast<const uint32_t*>(&lo);
+        redv[i].y = *reinterpret_cast<const uint32_t*>(&hi);
+        const uint4 word = make_uint4(redv[i].x, e, redv[i].y, e);
+        for (int s = 0; s < N; ++s)
+          if (s != rank) st_relaxed_sys_v4(t.ll2[s] + (int64_t)r * npair + p, word);
+      }
+    }
+  }
+  // residual add + RMSNorm of row r (identical arithmetic to the other variants / sq_add_rmsnorm)
+  float ss = 0.f;
+  uint2 v[MAXP];
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    const int p = tid + i * 256;
+    if (p < npair) {
+      const uint2 a = reinterpret_cast<const uint2*>(resid + (int64_t)r * hidden)[p];
+      const __half2 a0 = *reinterpret_cast<const __half2*>(&a.x), a1 = *reinterpret_cast<const __half2*>(&a.y);
+      const __half2 x0 = *reinterpret_cast<const __half2*>(&redv[i].x), x1 = *reinterpret_cast<const __half2*>(&redv[i].y);
+      const __half2 s0 = __floats2half2_rn(__low2float(a0) + __low2float(x0), __high2float(a0) + __high2float(x0));
+      const __half2 s1 = __floats2half2_rn(__low2float(a1) + __low2float(x1), __high2float(a1) + __high2float(x1));
+      const float f0 = __low2float(s0), f1 = __high2float(s0), f2 = __low2float(s1), f3 = __high2float(s1);
+      ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
+      v[i].x = *reinterpret_cast<const uint32_t*>(&s0);
+      v[i].y = *reinterpret_cast<const uint32_t*>(&s1);
+      reinterpret_cast<uint2*>(resid + (int64_t)r * hidden)[p] = v[i];
+    }
+  }
+  ss = block_sum<8>(ss, red);
+  const float inv = rsqrtf(ss / (float)hidden + eps);
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    const int p = tid + i * 256;
+    if (p < npair) {
+      const uint2 wv = reinterpret_cast<const uint2*>(w)[p];
+      const __half2 w0 = *reinterpret_cast<const __half2*>(&wv.x), w1 = *reinterpret_cast<const __half2*>(&wv.y);
+      const __half2 s0 = *reinterpret_cast<const __half2*>(&v[i].x), s1 = *reinterpret_cast<const __half2*>(&v[i].y);
+      const __half2 o0 = __floats2half2_rn(__low2float(w0) * h2f(f2h(__low2float(s0) * inv)), __high2float(w0) * h2f(f2h(__high2float(s0) * inv)));
+      const __half2 o1 = __floats2half2_rn(__low2float(w1) * h2f(f2h(__low2float(s1) * inv)), __high2float(w1) * h2f(f2h(__high2float(s1) * inv)));
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&o0);
+      o.y = *reinterpret_cast<const uint32_t*>(&o1);
+      reinterpret_cast<uint2*>(out + (int64_t)r * hidden)[p] = o;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t ticket = atomicAdd(t.epoch + 1, 1u);
+    if (ticket == gridDim.x - 1) {
+      t.epoch[1] = 0u;
+      __threadfence();
+      t.epoch[0] = e;
+    }
+  }
+}
+
 }  // namespace sq
 
 using namespace sq;
@@ -498,5 +634,31 @@ extern "C" int sq_tp_allreduce3_add_rmsnorm(sq_half* resid, const sq_half* proj_
   else if (nvec <= 1024) launch_k(tp_allreduce3_add_rmsnorm_kernel<4>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
   else launch_k(tp_allreduce3_add_rmsnorm_kernel<8>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
   SQ_CHECK_LAUNCH("sq_tp_allreduce3_add_rmsnorm");
+  return SQ_OK;
+}
+
+extern "C" int sq_tp_allreduce_ll_add_rmsnorm(sq_half* resid, const sq_half* proj_local, void* const* host_ll1_ptrs,
+                                              void* const* host_ll2_ptrs, uint32_t* epoch, int rank, int N, int rows_max,
+                                              int own_max, const sq_half* weight, sq_half* out, int n, int hidden, float eps,
+                                              void* stream) {
+  SQ_CHECK_ARG(N >= 2 && N <= 8 && rank >= 0 && rank < N, "sq_tp_allreduce_ll_add_rmsnorm: bad rank/N %d/%d", rank, N);
+  SQ_CHECK_ARG(hidden % 4 == 0 && hidden <= 256 * 4 * 8, "sq_tp_allreduce_ll_add_rmsnorm: hidden=%d unsupported", hidden);
+  SQ_CHECK_ARG(n <= rows_max && (n + N - 1) / N <= own_max, "sq_tp_allreduce_ll_add_rmsnorm: n=%d exceeds the LL areas", n);
+  if (n == 0) return SQ_OK;
+  TpLLArgs t;
+  t.proj = (const __half*)proj_local;
+  for (int i = 0; i < 8; ++i) {
+    t.ll1[i] = i < N ? (uint4*)host_ll1_ptrs[i] : nullptr;
+    t.ll2[i] = i < N ? (uint4*)host_ll2_ptrs[i] : nullptr;
+  }
+  t.epoch = epoch; t.rank = rank; t.N = N; t.rows_max = rows_max; t.own_max = own_max;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int npair = hidden / 4;
+  __half* r = (__half*)resid; const __half* w = (const __half*)weight; __half* o = (__half*)out;
+  if (npair <= 256) launch_k(tp_allreduce_ll_add_rmsnorm_kernel<1>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
+  else if (npair <= 512) launch_k(tp_allreduce_ll_add_rmsnorm_kernel<2>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
+  else if (npair <= 1024) launch_k(tp_allreduce_ll_add_rmsnorm_kernel<4>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
+  else launch_k(tp_allreduce_ll_add_rmsnorm_kernel<8>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
+  SQ_CHECK_LAUNCH("sq_tp_allreduce_ll_add_rmsnorm");
   return SQ_OK;
 }

@@ -36,7 +36,12 @@ class PeerBuffers:
         self.push_rows = min(n_max, 256)
         recv_bytes = self.N * self.push_rows * hidden * 2
         pflag_bytes = ((self.N * self.push_rows * 4 + 1023) // 1024) * 1024
-        total = 4 * part + 2 * self.FLAG_BYTES + 2 * rowflag_bytes + 2 * recv_bytes + pflag_bytes
+        # LL two-shot (small payloads): gather area (N sources x rows owned) and reduced-row area, 2 bytes of slot per byte of
+        # payload, per buffer parity
+        self.ll_own = (self.push_rows + self.N - 1) // self.N
+        ll1_bytes = self.N * self.ll_own * hidden * 4
+        ll2_bytes = self.push_rows * hidden * 4
+        total = 4 * part + 2 * self.FLAG_BYTES + 2 * rowflag_bytes + 2 * recv_bytes + pflag_bytes + 2 * (ll1_bytes + ll2_bytes)
         # one-shot (every rank pulls all partials) below 4 ranks, two-shot (reduce-scatter + all-gather in one kernel)
         # from 4 ranks up; SQ_TP_SHOT=1|2 overrides
         import os
@@ -46,6 +51,9 @@ class PeerBuffers:
         # than the pull kernel (4.02 vs 3.68 ms / step; 18.5 vs 12.7 us per reduction) -- the system fence between the remote
         # stores and the flag costs the round trip that the pull spends on its loads.
         self.push_ok = shot == "3"
+        # shot 4 = LL two-shot (data and epoch in one 8-byte store, readers poll): the default for small payloads
+        self.ll_ok = shot in ("", "4")
+        self.ll_bytes_max = 4 << 20
         self.push_bytes_max = 8 << 20
         base = C.c_void_p()
         check(lib.sq_tp_alloc(C.byref(base), total), "sq_tp_alloc")
@@ -75,6 +83,10 @@ class PeerBuffers:
         rv0 = rf0 + 2 * rowflag_bytes
         self.recv_ptrs = [arr(*[(b + rv0 + w * recv_bytes) for b in self.bases] + [None] * (8 - self.N)) for w in range(2)]
         self.pflag_ptrs = arr(*[(b + rv0 + 2 * recv_bytes) for b in self.bases] + [None] * (8 - self.N))
+        ll0 = rv0 + 2 * recv_bytes + pflag_bytes
+        self.ll1_ptrs = [arr(*[(b + ll0 + w * (ll1_bytes + ll2_bytes)) for b in self.bases] + [None] * (8 - self.N)) for w in range(2)]
+        self.ll2_ptrs = [arr(*[(b + ll0 + w * (ll1_bytes + ll2_bytes) + ll1_bytes) for b in self.bases] + [None] * (8 - self.N))
+                         for w in range(2)]
         self.buf = [torch.as_tensor(_CudaArray(self.base + w * part, (n_max, hidden)), device=self.device) for w in range(2)]
         assert self.buf[0].data_ptr() == self.base and self.buf[0].dtype == torch.float16
         dist.barrier(group=group)                      # every rank has mapped every peer before the first kernel runs
@@ -82,6 +94,12 @@ class PeerBuffers:
     def allreduce_add_rmsnorm(self, which: int, resid: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, n: int,
                               eps: float):
         """resid += sum over ranks of partial buffer `which`; out = rmsnorm(resid) * weight  (one kernel per rank)."""
+        if self.ll_ok and n <= self.push_rows and n * self.hidden * 2 <= self.ll_bytes_max:
+            check(_lib.load().sq_tp_allreduce_ll_add_rmsnorm(ptr(resid), self.buf[which].data_ptr(), self.ll1_ptrs[which],
+                                                             self.ll2_ptrs[which], self.epoch_ptr, self.rank, self.N,
+                                                             self.push_rows, self.ll_own, ptr(weight), ptr(out), n, self.hidden,
+                                                             eps, stream_ptr()), "sq_tp_allreduce_ll_add_rmsnorm")
+            return
         if self.push_ok and n <= self.push_rows and (self.N - 1) * n * self.hidden * 2 <= self.push_bytes_max:
             check(_lib.load().sq_tp_allreduce3_add_rmsnorm(ptr(resid), self.buf[which].data_ptr(), self.recv_ptrs[which],
                                                            self.pflag_ptrs, self.epoch_ptr, self.rank, self.N, self.push_rows,

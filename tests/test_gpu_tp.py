@@ -90,10 +90,11 @@ def _worker(rank, world, port, q, variant="tiny"):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("variant,shot", [("tiny", "1"), ("tiny", "2"), ("tiny", "3"), ("70b-8l", "2"), ("70b-8l", "3")])
+@pytest.mark.parametrize("variant,shot", [("tiny", "1"), ("tiny", "2"), ("tiny", "3"), ("tiny", "4"), ("70b-8l", "2"), ("70b-8l", "4")])
 def test_tp2_decode_matches_single_gpu(variant, shot):
     """shot = fused all-reduce flavour (csrc/sq_tp.cu): 1 = one-shot pull, 2 = two-shot reduce-scatter + all-gather in one
-    kernel, 3 = one-shot push for small payloads (opt-in; larger ones fall back to pull / two-shot, as the 768-row
+    kernel, 4 = LL two-shot (data + epoch in one 8-byte store, readers poll; the default for small payloads),
+    3 = one-shot push for small payloads (opt-in; larger ones fall back to pull / two-shot, as the 768-row
     verify of the 70B-shaped variant does) -- all must work at any N."""
     import torch.multiprocessing as mp
     os.environ["SQ_TP_SHOT"] = shot                   # inherited by the spawned ranks
