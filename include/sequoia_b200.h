@@ -261,10 +261,20 @@ int sq_tp_allreduce3_add_rmsnorm(sq_half* resid, const sq_half* proj_local, void
 /* LL two-shot for small payloads: every 8-byte word crossing NVLink carries two halfs + the reduction's epoch (one atomic
  * store), readers poll the words they need -- no flags, no fences, two one-way trips.  host_ll1_ptrs[r]: gather area on rank r,
  * (N, own_max, hidden/4) 16-byte pairs; host_ll2_ptrs[r]: reduced-row area on rank r, (rows_max, hidden/4) pairs; both for this
- * buffer parity, zero-initialised.  Row r is owned by rank r %% N. */
+ * buffer parity, zero-initialised.  Row r is owned by rank r %% N.  own_max == rows_max selects the ONE-shot form (every rank
+ * pushes its row to every peer's gather slot and reduces locally: one trip, (N-1) x the bytes; meant for N <= 3). */
 int sq_tp_allreduce_ll_add_rmsnorm(sq_half* resid, const sq_half* proj_local, void* const* host_ll1_ptrs,
                                    void* const* host_ll2_ptrs, uint32_t* epoch, int rank, int N, int rows_max, int own_max,
                                    const sq_half* weight, sq_half* out, int n, int hidden, float eps, void* stream);
+
+/* Driver -> follower messages over peer memory as LL words (4 bytes of payload + the message's epoch per 8-byte store; the
+ * reader polls): replaces the NCCL broadcasts of tokens / position ids / state / accept list.  host_mbox_ptrs[i]: the channel's
+ * mailbox on follower i (2 x cap_words 8-byte words, zero-initialised, double-buffered by epoch parity); `epoch`: this rank's
+ * device counter for the channel.  Up to three segments of 4-byte words per message. */
+int sq_tp_ll_publish(void* const* host_mbox_ptrs, int n_peers, int cap_words, uint32_t* epoch, const void* src0, int words0,
+                     const void* src1, int words1, const void* src2, int words2, void* stream);
+int sq_tp_ll_consume(const void* mbox_local, int cap_words, uint32_t* epoch, uint32_t* err, void* dst0, int words0, void* dst1,
+                     int words1, void* dst2, int words2, void* stream);
 
 /* ---- fused draft forward (csrc/sq_draft.cu): one persistent cooperative kernel per tree level for small draft models
  * (Engine/Engine.py:158-164 replays a ~25-kernel graph per level; Tree/SpecTree.py:245-259).  Supported: head_dim 64,

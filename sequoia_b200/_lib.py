@@ -65,6 +65,8 @@ _SIGNATURES = {
     "sq_tp_allreduce2_add_rmsnorm": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp]),
     "sq_tp_allreduce3_add_rmsnorm": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, i32, f32, vp]),
     "sq_tp_allreduce_ll_add_rmsnorm": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, f32, vp]),
+    "sq_tp_ll_publish": (i32, [vp, i32, i32, vp, vp, i32, vp, i32, vp, i32, vp]),
+    "sq_tp_ll_consume": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, vp, i32, vp]),
     "sq_draft_workspace_bytes": (i64, [i32, i32]),
     "sq_draft_supported": (i32, [i32, i32, i32, i32, i32, i32, i32, i32]),
     "sq_draft_plan_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64]),

@@ -401,6 +401,8 @@ struct TpLLArgs {
   uint4* ll2[8];             // ll2[r] = reduced-row area on rank r: (rows_max, hidden/4 pairs)
   uint32_t* epoch;
   int rank, N, rows_max, own_max;
+  int oneshot;               // 1: every rank pushes its row to EVERY peer's gather slot [src][r] and reduces locally (one trip;
+                             //    (N-1) x 2 x payload on the wire: N <= 3); own_max == rows_max then
 };
 
 __device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
@@ -428,13 +430,25 @@ __global__ void __launch_bounds__(256) tp_allreduce_ll_add_rmsnorm_kernel(TpLLAr
   pdl_trigger();
   const uint32_t e = t.epoch[0] + 1;
   const int npair = hidden / 4;
-  const int owner = r % N, lrow = r / N;
+  const int owner = t.oneshot ? rank : r % N, lrow = t.oneshot ? r : r / N;
   uint2 mine[MAXP], redv[MAXP];
 #pragma unroll
   for (int i = 0; i < MAXP; ++i) {
     const int p = tid + i * 256;
     mine[i] = make_uint2(0u, 0u);
     if (p < npair) mine[i] = reinterpret_cast<const uint2*>(t.proj + (int64_t)r * hidden)[p];
+  }
+  if (t.oneshot) {
+    // one-shot: my partial row goes to every peer's gather slot [rank][r]; the reduction below polls the peers' rows
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+      const int p = tid + i * 256;
+      if (p < npair) {
+        const uint4 word = make_uint4(mine[i].x, e, mine[i].y, e);
+        for (int s = 0; s < N; ++s)
+          if (s != rank) st_relaxed_sys_v4(t.ll1[s] + ((int64_t)rank * t.own_max + lrow) * npair + p, word);
+      }
+    }
   }
   if (owner != rank) {
     // (1) push my partial row to the owner
@@ -468,9 +482,11 @@ __global__ void __launch_bounds__(256) tp_allreduce_ll_add_rmsnorm_kernel(TpLLAr
         const __half2 lo = __floats2half2_rn(acc[0], acc[1]), hi = __floats2half2_rn(acc[2], acc[3]);
         redv[i].x = *reinterpret_cast<const uint32_t*>(&lo);
         redv[i].y = *reinterpret_cast<const uint32_t*>(&hi);
-        const uint4 word = make_uint4(redv[i].x, e, redv[i].y, e);
-        for (int s = 0; s < N; ++s)
-          if (s != rank) st_relaxed_sys_v4(t.ll2[s] + (int64_t)r * npair + p, word);
+        if (!t.oneshot) {
+          const uint4 word = make_uint4(redv[i].x, e, redv[i].y, e);
+          for (int s = 0; s < N; ++s)
+            if (s != rank) st_relaxed_sys_v4(t.ll2[s] + (int64_t)r * npair + p, word);
+        }
       }
     }
   }
@@ -519,6 +535,64 @@ __global__ void __launch_bounds__(256) tp_allreduce_ll_add_rmsnorm_kernel(TpLLAr
       t.epoch[0] = e;
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Driver -> follower messages (tokens / position ids / state word before the target forward, accept list / state after the
+// walk) as LL words through peer memory instead of five NCCL broadcast kernels per step (11.5 us each inside the graph at
+// TP-8, profiles/r02_timeline_c2_tp8.md): ONE CTA on the driver writes every 4-byte word of up to three segments, paired with
+// this message's epoch, into each follower's mailbox; ONE CTA on each follower polls its mailbox and scatters the words into
+// its local tensors.  Mailboxes are double-buffered by epoch parity; epochs are per channel and live on the device.
+struct MsgSeg { const uint32_t* src; uint32_t* dst; int words; };
+
+__global__ void __launch_bounds__(256) tp_ll_publish_kernel(uint2* const mbox0, uint2* const mbox1, uint2* const mbox2,
+                                                            uint2* const mbox3, uint2* const mbox4, uint2* const mbox5,
+                                                            uint2* const mbox6, int n_peers, int cap_words, uint32_t* epoch,
+                                                            MsgSeg s0, MsgSeg s1, MsgSeg s2) {
+  pdl_wait();
+  pdl_trigger();
+  uint2* const boxes[7] = {mbox0, mbox1, mbox2, mbox3, mbox4, mbox5, mbox6};
+  const uint32_t e = epoch[0] + 1;
+  const int half = (int)(e & 1u) * cap_words;
+  const MsgSeg segs[3] = {s0, s1, s2};
+  int off = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int i = threadIdx.x; i < segs[k].words; i += 256) {
+      const uint32_t v = segs[k].src[i];
+      for (int p = 0; p < n_peers; ++p)
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(boxes[p] + half + off + i), "r"(v), "r"(e) : "memory");
+    }
+    off += segs[k].words;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) epoch[0] = e;
+}
+
+__global__ void __launch_bounds__(256) tp_ll_consume_kernel(const uint2* mbox, int cap_words, uint32_t* epoch, uint32_t* err,
+                                                            MsgSeg s0, MsgSeg s1, MsgSeg s2) {
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t e = epoch[0] + 1;
+  const uint2* box = mbox + (int)(e & 1u) * cap_words;
+  const MsgSeg segs[3] = {s0, s1, s2};
+  int off = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int i = threadIdx.x; i < segs[k].words; i += 256) {
+      const long long t0 = clock64();
+      uint2 v;
+      do {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(box + off + i) : "memory");
+        if (v.y != e && clock64() - t0 > 4000000000LL) { atomicExch(err, 5u); break; }
+      } while (v.y != e);
+      segs[k].dst[i] = v.x;
+    }
+    off += segs[k].words;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) epoch[0] = e;
 }
 
 }  // namespace sq
@@ -641,9 +715,11 @@ extern "C" int sq_tp_allreduce_ll_add_rmsnorm(sq_half* resid, const sq_half* pro
                                               void* const* host_ll2_ptrs, uint32_t* epoch, int rank, int N, int rows_max,
                                               int own_max, const sq_half* weight, sq_half* out, int n, int hidden, float eps,
                                               void* stream) {
+  // own_max == rows_max selects the one-shot form (gather slots for every row from every source)
+  const int oneshot = own_max == rows_max ? 1 : 0;
   SQ_CHECK_ARG(N >= 2 && N <= 8 && rank >= 0 && rank < N, "sq_tp_allreduce_ll_add_rmsnorm: bad rank/N %d/%d", rank, N);
   SQ_CHECK_ARG(hidden % 4 == 0 && hidden <= 256 * 4 * 8, "sq_tp_allreduce_ll_add_rmsnorm: hidden=%d unsupported", hidden);
-  SQ_CHECK_ARG(n <= rows_max && (n + N - 1) / N <= own_max, "sq_tp_allreduce_ll_add_rmsnorm: n=%d exceeds the LL areas", n);
+  SQ_CHECK_ARG(n <= rows_max && (oneshot || (n + N - 1) / N <= own_max), "sq_tp_allreduce_ll_add_rmsnorm: n=%d exceeds the LL areas", n);
   if (n == 0) return SQ_OK;
   TpLLArgs t;
   t.proj = (const __half*)proj_local;
@@ -651,7 +727,7 @@ extern "C" int sq_tp_allreduce_ll_add_rmsnorm(sq_half* resid, const sq_half* pro
     t.ll1[i] = i < N ? (uint4*)host_ll1_ptrs[i] : nullptr;
     t.ll2[i] = i < N ? (uint4*)host_ll2_ptrs[i] : nullptr;
   }
-  t.epoch = epoch; t.rank = rank; t.N = N; t.rows_max = rows_max; t.own_max = own_max;
+  t.epoch = epoch; t.rank = rank; t.N = N; t.rows_max = rows_max; t.own_max = own_max; t.oneshot = oneshot;
   cudaStream_t st = (cudaStream_t)stream;
   const int npair = hidden / 4;
   __half* r = (__half*)resid; const __half* w = (const __half*)weight; __half* o = (__half*)out;
@@ -660,5 +736,28 @@ extern "C" int sq_tp_allreduce_ll_add_rmsnorm(sq_half* resid, const sq_half* pro
   else if (npair <= 1024) launch_k(tp_allreduce_ll_add_rmsnorm_kernel<4>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
   else launch_k(tp_allreduce_ll_add_rmsnorm_kernel<8>, dim3(n), dim3(256), 0, st, t, r, w, o, hidden, eps);
   SQ_CHECK_LAUNCH("sq_tp_allreduce_ll_add_rmsnorm");
+  return SQ_OK;
+}
+
+extern "C" int sq_tp_ll_publish(void* const* host_mbox_ptrs, int n_peers, int cap_words, uint32_t* epoch, const void* src0,
+                                int words0, const void* src1, int words1, const void* src2, int words2, void* stream) {
+  SQ_CHECK_ARG(n_peers >= 1 && n_peers <= 7 && words0 >= 0 && words1 >= 0 && words2 >= 0 && words0 + words1 + words2 <= cap_words,
+               "sq_tp_ll_publish: %d peers, %d words exceed the mailbox (%d)", n_peers, words0 + words1 + words2, cap_words);
+  uint2* b[7];
+  for (int i = 0; i < 7; ++i) b[i] = i < n_peers ? (uint2*)host_mbox_ptrs[i] : nullptr;
+  MsgSeg s0{(const uint32_t*)src0, nullptr, words0}, s1{(const uint32_t*)src1, nullptr, words1}, s2{(const uint32_t*)src2, nullptr, words2};
+  launch_k(tp_ll_publish_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, b[0], b[1], b[2], b[3], b[4], b[5], b[6], n_peers,
+           cap_words, epoch, s0, s1, s2);
+  SQ_CHECK_LAUNCH("sq_tp_ll_publish");
+  return SQ_OK;
+}
+
+extern "C" int sq_tp_ll_consume(const void* mbox_local, int cap_words, uint32_t* epoch, uint32_t* err, void* dst0, int words0,
+                                void* dst1, int words1, void* dst2, int words2, void* stream) {
+  SQ_CHECK_ARG(words0 >= 0 && words1 >= 0 && words2 >= 0 && words0 + words1 + words2 <= cap_words,
+               "sq_tp_ll_consume: %d words exceed the mailbox (%d)", words0 + words1 + words2, cap_words);
+  MsgSeg s0{nullptr, (uint32_t*)dst0, words0}, s1{nullptr, (uint32_t*)dst1, words1}, s2{nullptr, (uint32_t*)dst2, words2};
+  launch_k(tp_ll_consume_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, (const uint2*)mbox_local, cap_words, epoch, err, s0, s1, s2);
+  SQ_CHECK_LAUNCH("sq_tp_ll_consume");
   return SQ_OK;
 }

@@ -8,6 +8,7 @@ peer-visible memory with `torch.mm(..., out=...)`."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -23,6 +24,7 @@ class _CudaArray:
 
 class PeerBuffers:
     FLAG_BYTES = 1024
+    MBOX_WORDS = 8192          # 4-byte payload words per message (tokens + position ids of M <= 2040 plus the state word)
 
     def __init__(self, group, device, n_max: int, hidden: int):
         lib = _lib.load()
@@ -38,13 +40,16 @@ class PeerBuffers:
         pflag_bytes = ((self.N * self.push_rows * 4 + 1023) // 1024) * 1024
         # LL two-shot (small payloads): gather area (N sources x rows owned) and reduced-row area, 2 bytes of slot per byte of
         # payload, per buffer parity
-        self.ll_own = (self.push_rows + self.N - 1) // self.N
+        # (N <= 3: one-shot form -- every row from every source, one NVLink trip; else rows owned by rank r % N, two trips)
+        self.ll_own = self.push_rows if self.N <= 3 else (self.push_rows + self.N - 1) // self.N
         ll1_bytes = self.N * self.ll_own * hidden * 4
         ll2_bytes = self.push_rows * hidden * 4
-        total = 4 * part + 2 * self.FLAG_BYTES + 2 * rowflag_bytes + 2 * recv_bytes + pflag_bytes + 2 * (ll1_bytes + ll2_bytes)
+        # mailboxes for the driver -> follower messages: 2 channels x 2 parities x MBOX_WORDS 8-byte LL words
+        mbox_bytes = 2 * 2 * self.MBOX_WORDS * 8
+        total = (4 * part + 2 * self.FLAG_BYTES + 2 * rowflag_bytes + 2 * recv_bytes + pflag_bytes + 2 * (ll1_bytes + ll2_bytes)
+                 + mbox_bytes)
         # one-shot (every rank pulls all partials) below 4 ranks, two-shot (reduce-scatter + all-gather in one kernel)
         # from 4 ranks up; SQ_TP_SHOT=1|2 overrides
-        import os
         shot = os.environ.get("SQ_TP_SHOT", "")
         self.two_shot = (shot == "2") or (shot != "1" and self.N >= 4)
         # shot 3 = one-shot PUSH for small payloads (<= 8 MB pushed per rank).  Opt-in: measured at TP-2 on c2 it is slower
@@ -87,6 +92,12 @@ class PeerBuffers:
         self.ll1_ptrs = [arr(*[(b + ll0 + w * (ll1_bytes + ll2_bytes)) for b in self.bases] + [None] * (8 - self.N)) for w in range(2)]
         self.ll2_ptrs = [arr(*[(b + ll0 + w * (ll1_bytes + ll2_bytes) + ll1_bytes) for b in self.bases] + [None] * (8 - self.N))
                          for w in range(2)]
+        mb0 = ll0 + 2 * (ll1_bytes + ll2_bytes)
+        self.mbox_local = [self.base + mb0 + ch * 2 * self.MBOX_WORDS * 8 for ch in range(2)]
+        self.mbox_peers = [arr(*([b + mb0 + ch * 2 * self.MBOX_WORDS * 8 for i, b in enumerate(self.bases) if i != self.rank]
+                                 + [None] * (8 - (self.N - 1)))) for ch in range(2)]
+        self.msg_epoch = torch.zeros(4, dtype=torch.int32, device=self.device)      # [channel] message counters of this rank
+        self.msg_on = os.environ.get("SQ_TP_MSG", "ll") == "ll"                      # SQ_TP_MSG=nccl keeps the NCCL broadcasts
         self.buf = [torch.as_tensor(_CudaArray(self.base + w * part, (n_max, hidden)), device=self.device) for w in range(2)]
         assert self.buf[0].data_ptr() == self.base and self.buf[0].dtype == torch.float16
         dist.barrier(group=group)                      # every rank has mapped every peer before the first kernel runs
@@ -115,6 +126,27 @@ class PeerBuffers:
         check(_lib.load().sq_tp_allreduce_add_rmsnorm(ptr(resid), self.proj_ptrs[which], self.flag_ptrs, self.epoch_ptr,
                                                       self.rank, self.N, ptr(weight), ptr(out), n, self.hidden, eps,
                                                       stream_ptr()), "sq_tp_allreduce_add_rmsnorm")
+
+    @staticmethod
+    def _words(t):
+        assert t.is_contiguous() and (t.numel() * t.element_size()) % 4 == 0
+        return t.numel() * t.element_size() // 4
+
+    def publish(self, channel: int, tensors):
+        """Rank 0: write `tensors` (<= 3) as LL words into every follower's mailbox of `channel` (one kernel)."""
+        ts = list(tensors) + [None] * (3 - len(tensors))
+        a = [(ptr(t), self._words(t)) if t is not None else (None, 0) for t in ts]
+        check(_lib.load().sq_tp_ll_publish(self.mbox_peers[channel], self.N - 1, self.MBOX_WORDS,
+                                           self.msg_epoch.data_ptr() + 4 * channel, a[0][0], a[0][1], a[1][0], a[1][1], a[2][0],
+                                           a[2][1], stream_ptr()), "sq_tp_ll_publish")
+
+    def consume(self, channel: int, tensors):
+        """Followers: poll the mailbox of `channel` and scatter the words into `tensors` (one kernel)."""
+        ts = list(tensors) + [None] * (3 - len(tensors))
+        a = [(ptr(t), self._words(t)) if t is not None else (None, 0) for t in ts]
+        check(_lib.load().sq_tp_ll_consume(self.mbox_local[channel], self.MBOX_WORDS, self.msg_epoch.data_ptr() + 4 * channel,
+                                           self.epoch_ptr + 8, a[0][0], a[0][1], a[1][0], a[1][1], a[2][0], a[2][1], stream_ptr()),
+              "sq_tp_ll_consume")
 
     def error(self) -> int:
         t = torch.as_tensor(_CudaArray(self.epoch_ptr, (4,), "<i4"), device=self.device)

@@ -32,10 +32,12 @@ MODE_REPLAY, MODE_EAGER, MODE_CAPTURE = 0, 1, 2
 class TPDriver:
     """Rank-0 side: control messages + the two in-graph broadcast points."""
 
-    def __init__(self, group, device):
+    def __init__(self, group, device, peer=None):
         self.group, self.device = group, torch.device(device)
         self.ctrl = torch.zeros(4, dtype=torch.int64, device=self.device)
         self.src = dist.get_global_rank(group, 0) if group is not dist.group.WORLD else 0
+        # peer-memory mailboxes (peer.PeerBuffers.publish / consume) instead of NCCL broadcasts for the in-graph messages
+        self.peer = peer if (peer is not None and peer.msg_on) else None
 
     def send_ctrl(self, op: int, a: int = 0, b: int = 0, mode: int = 0):
         self.ctrl.copy_(torch.tensor([op, a, b, mode], dtype=torch.int64), non_blocking=False)
@@ -49,18 +51,24 @@ class TPDriver:
         dist.barrier(group=self.group)
 
     def bcast_inputs(self, rt):
+        if self.peer is not None:
+            self.peer.publish(0, [rt.tokens, rt.position_ids, rt.state])
+            return
         dist.broadcast(rt.tokens, self.src, group=self.group)
         dist.broadcast(rt.position_ids, self.src, group=self.group)
         dist.broadcast(rt.state, self.src, group=self.group)
 
     def bcast_accept(self, rt):
+        if self.peer is not None:
+            self.peer.publish(1, [rt.accept_idx, rt.state])
+            return
         dist.broadcast(rt.accept_idx, self.src, group=self.group)
         dist.broadcast(rt.state, self.src, group=self.group)
 
 
 def attach_tp(draft_engine, target_engine, group):
     """Mark the (rank-0) target engine as tensor-parallel so Tree runtimes broadcast to the follower ranks."""
-    target_engine._tp_driver = TPDriver(group, target_engine.device)
+    target_engine._tp_driver = TPDriver(group, target_engine.device, getattr(target_engine.engine.runner, "peer", None))
     return target_engine._tp_driver
 
 
@@ -96,18 +104,26 @@ class TPFollower:
         self.src = 0
         self.graph = None
         self.use_graphs = True
+        peer = getattr(target_engine.engine.runner, "peer", None)
+        self.peer = peer if (peer is not None and peer.msg_on) else None
 
     def _mask_kw(self):
         return dict(tree_bits=self.st.tree_bits, tree_words=self.st.tree_words, tree_size=self.st.S)
 
     def _recv_inputs(self):
+        if self.peer is not None:
+            self.peer.consume(0, [self.tokens, self.position_ids, self.state])
+            return
         dist.broadcast(self.tokens, self.src, group=self.group)
         dist.broadcast(self.position_ids, self.src, group=self.group)
         dist.broadcast(self.state, self.src, group=self.group)
 
     def _recv_accept_and_gather(self):
-        dist.broadcast(self.accept_idx, self.src, group=self.group)
-        dist.broadcast(self.state, self.src, group=self.group)
+        if self.peer is not None:
+            self.peer.consume(1, [self.accept_idx, self.state])
+        else:
+            dist.broadcast(self.accept_idx, self.src, group=self.group)
+            dist.broadcast(self.state, self.src, group=self.group)
         self.target.engine.kv_cache.gather_from_state(self.accept_idx, self.state, max(self.st.max_depth, 1))
 
     def _steady(self):
