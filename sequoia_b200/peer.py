@@ -56,10 +56,11 @@ class PeerBuffers:
         # than the pull kernel (4.02 vs 3.68 ms / step; 18.5 vs 12.7 us per reduction) -- the system fence between the remote
         # stores and the flag costs the round trip that the pull spends on its loads.
         self.push_ok = shot == "3"
-        # shot 4 = LL (data and epoch in one 8-byte store, readers poll).  Default for small payloads from 4 ranks up (two
-        # NVLink trips instead of the pull two-shot's four); below 4 ranks the one-shot pull measured as fast or faster
-        # (TP-2, c2: 3.69 ms / step pull vs 3.75 LL one-shot), so it stays the default there.
-        self.ll_ok = shot == "4" or (shot == "" and self.N >= 4)
+        # shot 4 = LL (data and epoch in one 8-byte store, readers poll).  Measured on c2 (128 rows x 4096, 1 MB payload,
+        # profiles/r02_bench_c2_tp*.json): TP-2 one-shot pull 3.69 ms / step vs LL 3.75; TP-4 LL 3.53 vs two-shot pull 3.68;
+        # TP-8 two-shot pull 3.40 vs LL 3.69 (LL doubles the bytes, and at 8 ranks each owner gathers 7 x 256 KB).  Defaults
+        # follow the measurements: pull below 4 ranks, LL for 4..7 ranks, two-shot pull at 8.
+        self.ll_ok = shot == "4" or (shot == "" and 4 <= self.N < 8)
         self.ll_bytes_max = 4 << 20
         self.push_bytes_max = 8 << 20
         base = C.c_void_p()
