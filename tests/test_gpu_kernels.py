@@ -22,6 +22,14 @@ def ops():
     return _ops
 
 
+def _log(line: str):
+    """append a measured number to gpurun_out/logit_err.log (evidence copied to profiles/)"""
+    out = os.path.join(os.path.dirname(G), "..", "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "logit_err.log"), "a") as f:
+        f.write(line + "\n")
+
+
 def ulp_close(a: torch.Tensor, b: torch.Tensor, ulps: int = 1, atol: float = 0.0):
     """|a-b| <= ulps * fp16 spacing at max(|a|,|b|) (+ atol)."""
     a32, b32 = a.float().cpu(), b.float().cpu()
@@ -854,14 +862,12 @@ def test_fused_draft_forward_matches_multi_kernel_path(hidden, inter, heads, lay
             v_exact = (w["model.layers.0.self_attn.v_proj.weight"].float() @ xn).to(F16).view(heads, -1)
             bad_ref, _ = ulp_close(va[0, 0, :, 0].cpu(), v_exact, 1, atol=1e-4)
             bad_fused, _ = ulp_close(vb[0, 0, :, 0].cpu(), v_exact, 1, atol=1e-4)
-            with open(os.path.join(os.path.dirname(G), "..", "gpurun_out", "logit_err.log"), "a") as f:
-                f.write(f"fused draft (h={hidden}): layer-0 V row of the root vs fp32: multi-kernel path {bad_ref} / fused {bad_fused} of "
-                        f"{v_exact.numel()} values beyond 1 ulp\n")
+            _log(f"fused draft (h={hidden}): layer-0 V row of the root vs fp32: multi-kernel path {bad_ref} / fused {bad_fused} of "
+                 f"{v_exact.numel()} values beyond 1 ulp")
             assert bad_fused <= v_exact.numel() * 5e-3, f"fused draft kernel: {bad_fused} V values beyond 1 ulp of the exact product"
         nbad, _ = ulp_close(va, vb, 2, atol=2e-3)
         assert nbad <= va.numel() * 5e-3, f"level n0={n0}: {nbad} appended V values beyond 2 ulp"
         ka, kb = ref.k_cache[:, :, :, sl].float(), fused.k_cache[:, :, :, sl].float()
         kerr = ((ka - kb).abs().amax(dim=-1) / ka.abs().amax(dim=-1).clamp(min=1e-3)).max().item()
         assert kerr < 4e-3, f"level n0={n0}: appended K rows differ by {kerr:.3e} of the row's max"
-    with open(os.path.join(os.path.dirname(G), "..", "gpurun_out", "logit_err.log"), "a") as f:
-        f.write(f"fused draft forward [{mode}] (h={hidden} I={inter} L={layers}): max rel logit diff vs the multi-kernel path {worst:.3e}\n")
+    _log(f"fused draft forward [{mode}] (h={hidden} I={inter} L={layers}): max rel logit diff vs the multi-kernel path {worst:.3e}")
