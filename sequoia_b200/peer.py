@@ -135,6 +135,10 @@ class PeerBuffers:
         assert t.is_contiguous() and (t.numel() * t.element_size()) % 4 == 0
         return t.numel() * t.element_size() // 4
 
+    def fits(self, tensors) -> bool:
+        """True if the message fits a mailbox (else the caller keeps the NCCL broadcasts; both sides see the same sizes)."""
+        return sum(self._words(t) for t in tensors) <= self.MBOX_WORDS
+
     def publish(self, channel: int, tensors):
         """Rank 0: write `tensors` (<= 3) as LL words into every follower's mailbox of `channel` (one kernel)."""
         ts = list(tensors) + [None] * (3 - len(tensors))

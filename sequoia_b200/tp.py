@@ -51,7 +51,7 @@ class TPDriver:
         dist.barrier(group=self.group)
 
     def bcast_inputs(self, rt):
-        if self.peer is not None:
+        if self.peer is not None and self.peer.fits([rt.tokens, rt.position_ids, rt.state]):
             self.peer.publish(0, [rt.tokens, rt.position_ids, rt.state])
             return
         dist.broadcast(rt.tokens, self.src, group=self.group)
@@ -59,7 +59,7 @@ class TPDriver:
         dist.broadcast(rt.state, self.src, group=self.group)
 
     def bcast_accept(self, rt):
-        if self.peer is not None:
+        if self.peer is not None and self.peer.fits([rt.accept_idx, rt.state]):
             self.peer.publish(1, [rt.accept_idx, rt.state])
             return
         dist.broadcast(rt.accept_idx, self.src, group=self.group)
@@ -111,7 +111,7 @@ class TPFollower:
         return dict(tree_bits=self.st.tree_bits, tree_words=self.st.tree_words, tree_size=self.st.S)
 
     def _recv_inputs(self):
-        if self.peer is not None:
+        if self.peer is not None and self.peer.fits([self.tokens, self.position_ids, self.state]):
             self.peer.consume(0, [self.tokens, self.position_ids, self.state])
             return
         dist.broadcast(self.tokens, self.src, group=self.group)
@@ -119,7 +119,7 @@ class TPFollower:
         dist.broadcast(self.state, self.src, group=self.group)
 
     def _recv_accept_and_gather(self):
-        if self.peer is not None:
+        if self.peer is not None and self.peer.fits([self.accept_idx, self.state]):
             self.peer.consume(1, [self.accept_idx, self.state])
         else:
             dist.broadcast(self.accept_idx, self.src, group=self.group)
