@@ -756,3 +756,23 @@ def simulation_fast(draft: EngineOracle, target: EngineOracle, prompts: Sequence
         draft.clear_kv()
         target.clear_kv()
     return num_decoding_steps, num_large_model_steps, traces
+
+
+def top_p_filter_integer(logits: torch.Tensor, top_p: float, T: float) -> torch.Tensor:
+    """The algorithm of the `sq_top_p_filter` kernel (csrc/sq_sampling.cu) restated on the CPU -- TEST INFRASTRUCTURE: it lets
+    the CPU suite check the kernel's arithmetic (exact integer masses instead of a sorted fp16 cumsum) against the reference's
+    golden vector (utils.py:65-77).  fp16 probabilities are integer multiples of 2^-24, so the mass ranked before a token is
+    an exact integer S; the token is removed iff fp16(S * 2^-24) > fp16(top_p).  Ranking: value descending, index ascending."""
+    out = logits.clone()
+    tp = float(torch.tensor(top_p, dtype=torch.float16))
+    for r in range(logits.shape[0]):
+        xt = (logits[r].float() * (1.0 / T)).to(torch.float16)                  # what torch's CUDA div-by-scalar computes
+        p = softmax(xt.float(), dim=-1).to(torch.float16)
+        w = (p.double() * 16777216.0).round().to(torch.int64)                   # exact
+        order = sorted(range(xt.numel()), key=lambda i: (-float(xt[i]), i))
+        before = 0
+        for i in order:
+            if float(torch.tensor(before / 16777216.0, dtype=torch.float32).to(torch.float16)) > tp:
+                out[r, i] = float("-inf")
+            before += int(w[i])
+    return out
