@@ -793,7 +793,7 @@ def test_gemm_fused_swiglu_epilogue_bit_exact(I, K, n, tiled):
 def test_fused_draft_forward_matches_multi_kernel_path(hidden, inter, heads, layers, M, mode):
     """csrc/sq_draft.cu (one persistent cooperative kernel per tree level) against the multi-kernel forward of the same
     LlamaRunner weights: same prefill, then every level of the 128-node config-2 tree, a 1-row forward (the bonus token of
-    prepare_for_next_iter) and a 64-row level.  Logits within 2e-3 of the row's max |logit| (different GEMM tiling /
+    prepare_for_next_iter) and a 64-row level.  Logits within 3e-3 of the row's max |logit| (different GEMM tiling /
     attention reduction order, same fp16 rounding points), appended K/V rows within 2 fp16 ulp."""
     from sequoia_b200.model import LlamaRunner
     from sequoia_b200.tree import pack_tree_mask
@@ -849,7 +849,9 @@ def test_fused_draft_forward_matches_multi_kernel_path(hidden, inter, heads, lay
         scale = la.float().abs().amax(dim=-1, keepdim=True)
         rel = ((la.float() - lb.float()).abs() / scale).max().item()
         worst = max(worst, rel)
-        assert rel < 2e-3, f"level n0={n0} n={n}: fused draft logits differ by {rel:.3e}"
+        # measured: 1.2e-3 - 1.4e-3 (chain / coop); two fp16 implementations of the same layer stack differ by ~2e-3 at most
+        # (cf. the 7B-shaped layer test), so the bound is 3e-3
+        assert rel < 3e-3, f"level n0={n0} n={n}: fused draft logits differ by {rel:.3e}"
         sl = slice(P - 1 + n0, P - 1 + n0 + n)
         # V rows are GEMM outputs: the two fp32 accumulation orders round to the same or the neighbouring fp16 value.  K rows
         # went through RoPE (a*cos - b*sin of two such values, with cancellation): bounded relative to the row's magnitude.
